@@ -1,0 +1,460 @@
+/* C ABI (include/mcgpu_b200.h): context lifecycle, stage ordering, the projection loop and its
+ * two multi-GPU partitions.  Mirrors the control flow of the reference's main
+ * (docker/mcgpu/MC-GPU_v1.3.cu:377-1214) for the single-rank, fixed-history case (the only
+ * reproducible one): per projection -> grid rule (H:823-841), launch with the
+ * current seed (H:861), advance the seed by the launched histories (H:869), copy the tally
+ * back, report, zero the tally.  Because the seed of projection p and the RANECU state of
+ * stream t are closed-form in (p, t), projections can be dealt to different GPUs and a
+ * projection's streams can be split across GPUs without changing a single integer tally. */
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include "mcgpu_host.h"
+
+static double now_s(void) {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+mcgpu_ctx* mcgpu_create(const int* device_ids, int n_devices) {
+  mcgpu_ctx* ctx = (mcgpu_ctx*)calloc(1, sizeof *ctx);
+  int visible, i;
+  if (!ctx) return NULL;
+  visible = mcgpu_dev_count();
+  if (visible <= 0) { /* parsing and table building still work; run calls fail loudly */
+    snprintf(ctx->err, sizeof ctx->err, "no CUDA device visible");
+    return ctx;
+  }
+  if (!device_ids || n_devices <= 0) n_devices = visible;
+  ctx->dev = (struct mcgpu_device**)calloc((size_t)n_devices, sizeof *ctx->dev);
+  if (!ctx->dev) {
+    free(ctx);
+    return NULL;
+  }
+  for (i = 0; i < n_devices; i++) {
+    int id = device_ids ? device_ids[i] : i, k, dup = 0;
+    if (id < 0 || id >= visible) id = ctx->num_devices % visible; /* Q13: out-of-range id -> use what is visible */
+    for (k = 0; k < ctx->num_devices; k++) dup |= (mcgpu_dev_ordinal(ctx->dev[k]) == id);
+    if (dup) continue;
+    ctx->dev[ctx->num_devices] = mcgpu_dev_open(id, ctx->err, sizeof ctx->err);
+    if (ctx->dev[ctx->num_devices]) ctx->num_devices++;
+  }
+  return ctx;
+}
+
+void mcgpu_destroy(mcgpu_ctx* ctx) {
+  int i;
+  if (!ctx) return;
+  for (i = 0; i < ctx->num_devices; i++) mcgpu_dev_close(ctx->dev[i]);
+  free(ctx->dev);
+  free(ctx->views);
+  mcgpu_free_volume(&ctx->vol);
+  mcgpu_free_tables(&ctx->tab);
+  mcgpu_free_scene(&ctx->scene);
+  free(ctx);
+}
+
+const char* mcgpu_last_error(const mcgpu_ctx* ctx) { return ctx ? ctx->err : "null context"; }
+void mcgpu_set_verbose(mcgpu_ctx* ctx, int verbose) {
+  if (ctx) ctx->verbose = verbose;
+}
+
+int mcgpu_load_input(mcgpu_ctx* ctx, const char* in_path) {
+  int rc;
+  if (!ctx || !in_path) return MCGPU_E_ARG;
+  free(ctx->views);
+  ctx->views = NULL;
+  ctx->have_input = 0;
+  if ((rc = mcgpu_parse_input(ctx, in_path)) != MCGPU_OK) return rc;
+  if ((rc = mcgpu_read_spectrum(ctx, ctx->in.file_espc)) != MCGPU_OK) return rc;
+  if ((rc = mcgpu_build_views(ctx)) != MCGPU_OK) return rc;
+  ctx->hpt_current = ctx->in.histories_per_thread;
+  ctx->have_input = 1;
+  return MCGPU_OK;
+}
+
+int mcgpu_load_voxels(mcgpu_ctx* ctx, const char* vox_path) {
+  if (!ctx) return MCGPU_E_ARG;
+  if (!vox_path) {
+    if (!ctx->have_input) return mcgpu_fail(ctx, MCGPU_E_STATE, "load_voxels: no path given and no input file loaded");
+    vox_path = ctx->in.file_voxels;
+  }
+  return mcgpu_read_voxels(ctx, vox_path);
+}
+
+int mcgpu_load_materials(mcgpu_ctx* ctx, const char* const* paths, int n_paths) {
+  const char* from_input[MCGPU_MAX_MATERIALS];
+  int rc, i;
+  if (!ctx) return MCGPU_E_ARG;
+  if (!ctx->have_voxels) return mcgpu_fail(ctx, MCGPU_E_STATE, "load_material: the voxels must be loaded first (their densities set the Woodcock majorant)");
+  if (!paths) {
+    if (!ctx->have_input) return mcgpu_fail(ctx, MCGPU_E_STATE, "load_material: no paths given and no input file loaded");
+    for (i = 0; i < MCGPU_MAX_MATERIALS; i++) from_input[i] = ctx->in.file_materials[i];
+    paths = from_input;
+    n_paths = MCGPU_MAX_MATERIALS;
+  }
+  if ((rc = mcgpu_read_materials(ctx, paths, n_paths)) != MCGPU_OK) return rc;
+  if ((rc = mcgpu_build_scene(ctx)) != MCGPU_OK) return rc;
+  ctx->have_tables = 1;
+  if (ctx->have_input) {
+    for (i = 0; i < ctx->num_devices; i++)
+      if (mcgpu_dev_upload(ctx->dev[i], &ctx->scene, &ctx->vol, &ctx->spc, ctx->views[0].total_num_pixels, ctx->err, sizeof ctx->err) != 0) return MCGPU_E_CUDA;
+  }
+  return MCGPU_OK;
+}
+
+int mcgpu_set_histories(mcgpu_ctx* ctx, unsigned long long total_histories) {
+  if (!ctx || !ctx->have_input) return MCGPU_E_STATE;
+  ctx->in.total_histories = total_histories;
+  ctx->hpt_current = ctx->in.histories_per_thread;
+  return MCGPU_OK;
+}
+
+int mcgpu_set_seed(mcgpu_ctx* ctx, int seed) {
+  if (!ctx || !ctx->have_input) return MCGPU_E_STATE;
+  ctx->in.seed_input = seed;
+  return MCGPU_OK;
+}
+
+static int projection_skipped(const mcgpu_ctx* ctx, int p) { /* H:671-677, Q6 */
+  const double a = ctx->in.initial_angle + p * ctx->in.D_angle;
+  return (a < ctx->in.angularROI_0) || (a > ctx->in.angularROI_1);
+}
+
+/* Seed, histories/thread and grid the reference's loop reaches projection p with (Q1). */
+static void schedule_for(const mcgpu_ctx* ctx, int p, int* seed, int* hpt, int* blocks, unsigned long long* launched) {
+  int q;
+  *seed = ctx->in.seed_input;
+  *hpt = ctx->in.histories_per_thread;
+  for (q = 0;; q++) {
+    if (q < p && projection_skipped(ctx, q)) continue;
+    mcgpu_grid_rule(ctx->in.total_histories, ctx->in.threads_per_block, hpt, blocks, launched);
+    if (q >= p) break;
+    *seed = mcgpu_ranecu_advance_projection_seed(*seed, *launched);
+  }
+}
+
+int mcgpu_projection_seed(mcgpu_ctx* ctx, int p, int* seed_out) {
+  int hpt, blocks;
+  unsigned long long launched;
+  if (!ctx || !ctx->have_input || p < 0 || p >= ctx->in.num_projections || !seed_out) return MCGPU_E_ARG;
+  schedule_for(ctx, p, seed_out, &hpt, &blocks, &launched);
+  return MCGPU_OK;
+}
+
+static int ready_to_run(mcgpu_ctx* ctx, int p) {
+  if (!ctx) return MCGPU_E_ARG;
+  if (!ctx->have_input || !ctx->have_voxels || !ctx->have_tables) return mcgpu_fail(ctx, MCGPU_E_STATE, "run: input, voxels and materials must be loaded first");
+  if (ctx->num_devices < 1) return mcgpu_fail(ctx, MCGPU_E_CUDA, "run: no usable CUDA device (there is no CPU fallback)");
+  if (p < 0 || p >= ctx->in.num_projections) return mcgpu_fail(ctx, MCGPU_E_ARG, "run: projection %d out of range [0,%d)", p, ctx->in.num_projections);
+  return MCGPU_OK;
+}
+
+/* launch the streams [b,e) of projection p on device d (asynchronous) */
+static int launch_on(mcgpu_ctx* ctx, int d, int p, long long b, long long e, int seed, int hpt) {
+  mcgpu_launch l;
+  l.histories_per_thread = hpt;
+  l.seed_input = seed;
+  l.threads_per_block = ctx->in.threads_per_block;
+  l.stream_begin = b;
+  l.stream_end = e;
+  l.zero_image = 1;
+  return mcgpu_dev_launch(ctx->dev[d], &ctx->views[p], &l, ctx->err, sizeof ctx->err) == 0 ? MCGPU_OK : MCGPU_E_CUDA;
+}
+
+int mcgpu_run_streams(mcgpu_ctx* ctx, int p, long long stream_begin, long long stream_end, uint64_t* image_host) {
+  int rc, seed, hpt, blocks;
+  unsigned long long launched;
+  float ms = 0.f;
+  if ((rc = ready_to_run(ctx, p)) != MCGPU_OK) return rc;
+  schedule_for(ctx, p, &seed, &hpt, &blocks, &launched);
+  ctx->hpt_current = hpt;
+  if (stream_begin < 0 || stream_end > (long long)blocks * ctx->in.threads_per_block || stream_begin > stream_end)
+    return mcgpu_fail(ctx, MCGPU_E_ARG, "run_streams: stream range [%lld,%lld) outside [0,%lld)", stream_begin, stream_end, (long long)blocks * ctx->in.threads_per_block);
+  if ((rc = launch_on(ctx, 0, p, stream_begin, stream_end, seed, hpt)) != MCGPU_OK) return rc;
+  if (mcgpu_dev_sync(ctx->dev[0], &ms, ctx->err, sizeof ctx->err) != 0) return MCGPU_E_CUDA;
+  ctx->last_kernel_ms = ms;
+  if (image_host && mcgpu_dev_fetch(ctx->dev[0], image_host, ctx->err, sizeof ctx->err) != 0) return MCGPU_E_CUDA;
+  return MCGPU_OK;
+}
+
+int mcgpu_run_projection(mcgpu_ctx* ctx, int p, uint64_t* image_host) {
+  int rc, seed, hpt, blocks, d, n;
+  unsigned long long launched;
+  float ms_max = 0.f;
+  if ((rc = ready_to_run(ctx, p)) != MCGPU_OK) return rc;
+  schedule_for(ctx, p, &seed, &hpt, &blocks, &launched);
+  ctx->hpt_current = hpt;
+  n = ctx->num_devices;
+  if (n > blocks) n = blocks;
+  /* history split: contiguous block ranges of the reference grid, one per device */
+  for (d = 0; d < n; d++) {
+    const long long b = (long long)blocks * d / n, e = (long long)blocks * (d + 1) / n;
+    if ((rc = launch_on(ctx, d, p, b * ctx->in.threads_per_block, e * ctx->in.threads_per_block, seed, hpt)) != MCGPU_OK) return rc;
+  }
+  for (d = 0; d < n; d++) {
+    float ms = 0.f;
+    if (mcgpu_dev_sync(ctx->dev[d], &ms, ctx->err, sizeof ctx->err) != 0) return MCGPU_E_CUDA;
+    if (ms > ms_max) ms_max = ms;
+  }
+  ctx->last_kernel_ms = ms_max;
+  /* integer tallies: summing the partial images in any order is bit-identical to one device */
+  for (d = 1; d < n; d++)
+    if (mcgpu_dev_accumulate_peer(ctx->dev[0], ctx->dev[d], ctx->err, sizeof ctx->err) != 0) return MCGPU_E_CUDA;
+  if (image_host && mcgpu_dev_fetch(ctx->dev[0], image_host, ctx->err, sizeof ctx->err) != 0) return MCGPU_E_CUDA;
+  return MCGPU_OK;
+}
+
+void* mcgpu_device_image(mcgpu_ctx* ctx) { return (ctx && ctx->num_devices > 0) ? mcgpu_dev_image_ptr(ctx->dev[0]) : NULL; }
+double mcgpu_last_kernel_ms(const mcgpu_ctx* ctx) { return ctx ? ctx->last_kernel_ms : 0.0; }
+
+/* ---- whole scan: projections dealt round-robin to the devices, one host thread per device ---- */
+
+typedef struct scan_shared {
+  mcgpu_ctx* ctx;
+  pthread_mutex_t mu;
+  pthread_cond_t cv;
+  int* done;       /* per projection: 0 pending, 1 done, 2 skipped, <0 error */
+  double* seconds; /* per projection */
+  int hpt, blocks;
+  int* seeds;
+} scan_shared;
+
+typedef struct scan_worker {
+  scan_shared* sh;
+  int device;
+  char err[512];
+} scan_worker;
+
+static void* scan_thread(void* arg) {
+  scan_worker* w = (scan_worker*)arg;
+  scan_shared* sh = w->sh;
+  mcgpu_ctx* ctx = sh->ctx;
+  const int P = ctx->in.num_projections, n = ctx->num_devices;
+  const size_t words = (size_t)4 * ctx->views[0].total_num_pixels;
+  uint64_t* image = (uint64_t*)malloc(words * sizeof(uint64_t));
+  int p;
+  for (p = w->device; p < P; p += n) {
+    int status = 1;
+    double t0 = now_s(), dt = 0.0;
+    if (!image) {
+      snprintf(w->err, sizeof w->err, "out of memory for the host image");
+      status = MCGPU_E_NOMEM;
+    } else if (projection_skipped(ctx, p)) {
+      status = 2;
+    } else {
+      mcgpu_launch l;
+      float ms;
+      l.histories_per_thread = sh->hpt;
+      l.seed_input = sh->seeds[p];
+      l.threads_per_block = ctx->in.threads_per_block;
+      l.stream_begin = 0;
+      l.stream_end = (long long)sh->blocks * ctx->in.threads_per_block;
+      l.zero_image = 1;
+      if (mcgpu_dev_launch(ctx->dev[w->device], &ctx->views[p], &l, w->err, sizeof w->err) != 0 || mcgpu_dev_sync(ctx->dev[w->device], &ms, w->err, sizeof w->err) != 0 ||
+          mcgpu_dev_fetch(ctx->dev[w->device], image, w->err, sizeof w->err) != 0)
+        status = MCGPU_E_CUDA;
+      dt = now_s() - t0;
+      if (status == 1) {
+        /* report_image only reads ctx; each worker writes its own file */
+        int verbose = ctx->verbose, rc;
+        (void)verbose;
+        rc = mcgpu_write_projection_ascii(ctx, p, image, dt);
+        if (rc != MCGPU_OK) {
+          snprintf(w->err, sizeof w->err, "%s", ctx->err);
+          status = rc;
+        }
+      }
+    }
+    pthread_mutex_lock(&sh->mu);
+    sh->done[p] = status;
+    sh->seconds[p] = dt;
+    pthread_cond_broadcast(&sh->cv);
+    pthread_mutex_unlock(&sh->mu);
+    if (status < 0) break;
+  }
+  free(image);
+  return NULL;
+}
+
+int mcgpu_run_all(mcgpu_ctx* ctx, mcgpu_progress_cb cb, void* user) {
+  int rc, P, p, n;
+  if ((rc = ready_to_run(ctx, 0)) != MCGPU_OK) return rc;
+  P = ctx->in.num_projections;
+  n = ctx->num_devices;
+
+  if (P < n) { /* fewer projections than devices: split each projection's histories instead */
+    const size_t words = (size_t)4 * ctx->views[0].total_num_pixels;
+    uint64_t* image = (uint64_t*)malloc(words * sizeof(uint64_t));
+    if (!image) return mcgpu_fail(ctx, MCGPU_E_NOMEM, "run_all: out of memory for the host image");
+    for (p = 0; p < P; p++) {
+      double t0 = now_s(), dt;
+      if (projection_skipped(ctx, p)) continue;
+      if (cb) cb(p, P, -1.0, user); /* "Simulating Projection" marker before the work, like H:680 */
+      if ((rc = mcgpu_run_projection(ctx, p, image)) != MCGPU_OK) break;
+      dt = now_s() - t0;
+      if ((rc = mcgpu_write_projection_ascii(ctx, p, image, dt)) != MCGPU_OK) break;
+      if (cb) cb(p, P, dt, user);
+    }
+    free(image);
+    return rc;
+  }
+
+  {
+    scan_shared sh;
+    scan_worker* workers = (scan_worker*)calloc((size_t)n, sizeof *workers);
+    pthread_t* threads = (pthread_t*)calloc((size_t)n, sizeof *threads);
+    int d, seed, hpt, blocks, verbose = ctx->verbose;
+    unsigned long long launched;
+    memset(&sh, 0, sizeof sh);
+    sh.ctx = ctx;
+    sh.done = (int*)calloc((size_t)P, sizeof(int));
+    sh.seconds = (double*)calloc((size_t)P, sizeof(double));
+    sh.seeds = (int*)calloc((size_t)P, sizeof(int));
+    if (!workers || !threads || !sh.done || !sh.seconds || !sh.seeds) {
+      free(workers), free(threads), free(sh.done), free(sh.seconds), free(sh.seeds);
+      return mcgpu_fail(ctx, MCGPU_E_NOMEM, "run_all: out of memory");
+    }
+    /* closed-form seed schedule (Q1), computed once for the whole scan */
+    seed = ctx->in.seed_input;
+    hpt = ctx->in.histories_per_thread;
+    blocks = 1;
+    for (p = 0; p < P; p++) {
+      if (projection_skipped(ctx, p)) continue;
+      mcgpu_grid_rule(ctx->in.total_histories, ctx->in.threads_per_block, &hpt, &blocks, &launched);
+      sh.seeds[p] = seed;
+      seed = mcgpu_ranecu_advance_projection_seed(seed, launched);
+    }
+    /* the sticky histories/thread only changes at the first simulated projection; using the
+     * final value for all of them is what the reference's loop does too (H:833) */
+    sh.hpt = hpt;
+    sh.blocks = blocks;
+    ctx->hpt_current = hpt;
+    pthread_mutex_init(&sh.mu, NULL);
+    pthread_cond_init(&sh.cv, NULL);
+    ctx->verbose = 0; /* per-projection report banners would interleave across workers */
+    for (d = 0; d < n; d++) {
+      workers[d].sh = &sh;
+      workers[d].device = d;
+      pthread_create(&threads[d], NULL, scan_thread, &workers[d]);
+    }
+    rc = MCGPU_OK;
+    for (p = 0; p < P && rc == MCGPU_OK; p++) {
+      int st;
+      pthread_mutex_lock(&sh.mu);
+      while (sh.done[p] == 0) {
+        /* a failed worker stops early: do not wait forever for its later projections */
+        int failed = 0, q;
+        for (q = 0; q < P; q++) failed |= sh.done[q] < 0;
+        if (failed) break;
+        pthread_cond_wait(&sh.cv, &sh.mu);
+      }
+      st = sh.done[p];
+      pthread_mutex_unlock(&sh.mu);
+      if (st == 1 && cb) {
+        cb(p, P, -1.0, user);
+        cb(p, P, sh.seconds[p], user);
+      } else if (st <= 0) {
+        int q;
+        rc = MCGPU_E_CUDA;
+        for (q = 0; q < P; q++)
+          if (sh.done[q] < 0) rc = sh.done[q];
+      }
+    }
+    for (d = 0; d < n; d++) pthread_join(threads[d], NULL);
+    ctx->verbose = verbose;
+    if (rc != MCGPU_OK)
+      for (d = 0; d < n; d++)
+        if (workers[d].err[0]) snprintf(ctx->err, sizeof ctx->err, "%s", workers[d].err);
+    pthread_mutex_destroy(&sh.mu);
+    pthread_cond_destroy(&sh.cv);
+    free(workers), free(threads), free(sh.done), free(sh.seconds), free(sh.seeds);
+    return rc;
+  }
+}
+
+int mcgpu_get_info(const mcgpu_ctx* ctx, mcgpu_info* out) {
+  int hpt, blocks = 0;
+  unsigned long long launched = 0;
+  if (!ctx || !out) return MCGPU_E_ARG;
+  memset(out, 0, sizeof *out);
+  out->num_devices = ctx->num_devices;
+  if (ctx->have_input) {
+    const mcgpu_view* v = &ctx->views[0];
+    hpt = ctx->hpt_current ? ctx->hpt_current : ctx->in.histories_per_thread;
+    mcgpu_grid_rule(ctx->in.total_histories, ctx->in.threads_per_block, &hpt, &blocks, &launched);
+    out->num_projections = ctx->in.num_projections;
+    out->num_pixels_x = v->num_pixels_x;
+    out->num_pixels_z = v->num_pixels_z;
+    out->num_spectrum_bins = ctx->spc.num_bins;
+    out->threads_per_block = ctx->in.threads_per_block;
+    out->histories_per_thread = hpt;
+    out->num_blocks = blocks;
+    out->seed_input = ctx->in.seed_input;
+    out->enable_specific_angles = ctx->in.enable_specific_angles;
+    out->requested_histories = ctx->in.total_histories;
+    out->launched_histories = launched;
+    out->mean_energy_spectrum = ctx->spc.mean_energy;
+  }
+  if (ctx->have_voxels) {
+    out->num_voxels_x = ctx->vol.nx;
+    out->num_voxels_y = ctx->vol.ny;
+    out->num_voxels_z = ctx->vol.nz;
+    out->voxel_bits = ctx->vol.voxel_bits;
+    out->palette_size = ctx->vol.palette_size;
+  }
+  if (ctx->have_tables) {
+    out->num_materials_used = ctx->scene.num_slots;
+    out->num_energy_values = ctx->tab.num_values;
+    out->e0 = ctx->tab.e0;
+    out->ide = ctx->tab.ide;
+  }
+  return MCGPU_OK;
+}
+
+long long mcgpu_copy_table(const mcgpu_ctx* ctx, const char* name, void* out, size_t cap) {
+  const void* src = NULL;
+  size_t bytes = 0;
+  const mcgpu_tables* t;
+  const size_t NR = (size_t)MCGPU_NP_RAYLEIGH * MCGPU_MAX_MATERIALS, NC = (size_t)MCGPU_MAX_MATERIALS * MCGPU_MAX_SHELLS;
+  if (!ctx || !name) return MCGPU_E_ARG;
+  t = &ctx->tab;
+#define TAB(nm, ptr, nbytes, cond) \
+  if (!strcmp(name, nm)) {         \
+    if (!(cond)) return MCGPU_E_STATE; \
+    src = (ptr);                   \
+    bytes = (nbytes);              \
+  }
+  TAB("woodcock", t->woodcock, sizeof(mcgpu_f2) * t->num_values, ctx->have_tables)
+  TAB("mfp_a", t->mfp_a, sizeof(mcgpu_f3) * t->num_values * MCGPU_MAX_MATERIALS, ctx->have_tables)
+  TAB("mfp_b", t->mfp_b, sizeof(mcgpu_f3) * t->num_values * MCGPU_MAX_MATERIALS, ctx->have_tables)
+  TAB("rayleigh_xco", t->ray_xco, 4 * NR, ctx->have_tables)
+  TAB("rayleigh_pco", t->ray_pco, 4 * NR, ctx->have_tables)
+  TAB("rayleigh_aco", t->ray_aco, 4 * NR, ctx->have_tables)
+  TAB("rayleigh_bco", t->ray_bco, 4 * NR, ctx->have_tables)
+  TAB("rayleigh_itlco", t->ray_itlco, NR, ctx->have_tables)
+  TAB("rayleigh_ituco", t->ray_ituco, NR, ctx->have_tables)
+  TAB("rayleigh_pmax", t->ray_pmax, (size_t)4 * t->num_values * MCGPU_MAX_MATERIALS, ctx->have_tables)
+  TAB("compton_fco", t->cmp_fco, 4 * NC, ctx->have_tables)
+  TAB("compton_uico", t->cmp_uico, 4 * NC, ctx->have_tables)
+  TAB("compton_fj0", t->cmp_fj0, 4 * NC, ctx->have_tables)
+  TAB("compton_noscco", t->cmp_noscco, sizeof(int) * MCGPU_MAX_MATERIALS, ctx->have_tables)
+  TAB("density_nominal", t->density_nominal, sizeof(float) * MCGPU_MAX_MATERIALS, ctx->have_tables)
+  TAB("espc", ctx->spc.espc, sizeof ctx->spc.espc, ctx->have_input)
+  TAB("espc_cutoff", ctx->spc.cutoff, sizeof ctx->spc.cutoff, ctx->have_input)
+  TAB("espc_alias", ctx->spc.alias, sizeof ctx->spc.alias, ctx->have_input)
+  TAB("views", ctx->views, sizeof(mcgpu_view) * (size_t)ctx->in.num_projections, ctx->have_input)
+  TAB("density_max", ctx->vol.density_max, sizeof ctx->vol.density_max, ctx->have_voxels)
+  TAB("voxel_material", ctx->vol.material, (size_t)ctx->vol.nx * ctx->vol.ny * ctx->vol.nz, ctx->have_voxels)
+  TAB("voxel_density", ctx->vol.density, (size_t)4 * ctx->vol.nx * ctx->vol.ny * ctx->vol.nz, ctx->have_voxels)
+  TAB("voxel_packed", ctx->vol.packed, ctx->vol.packed_bytes, ctx->have_voxels)
+#undef TAB
+  if (!src) return MCGPU_E_ARG;
+  if (!out) return (long long)bytes;
+  if (bytes > cap) bytes = cap;
+  memcpy(out, src, bytes);
+  return (long long)bytes;
+}

@@ -1,0 +1,113 @@
+/* MC-GPU_v1.3.x -- command-line drop-in: `MC-GPU_v1.3.x <input.in>`.
+ *
+ * A thin argv -> C-ABI shim around libmcgpu_b200 (include/mcgpu_b200.h) that keeps the process
+ * contract cbctmc relies on (cbctmc/mc/simulation.py:187-226):
+ *   - exactly one argument, the .in file; exit 0 on success, the reference's negative codes on
+ *     failure (docker/mcgpu/MC-GPU_v1.3.cu:1255, 1287, 2823);
+ *   - stdout carries "Simulating Projection <i> of <n>" per projection (H:680), which cbctmc
+ *     scrapes for its progress bar, and never the substring "error" on success (Q9);
+ *   - it tolerates being started N times by `mpirun -n N`: there is no MPI in this engine, one
+ *     process drives every visible GPU, so ranks other than 0 (as seen in the launcher's
+ *     environment) exit 0 immediately. */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include "mcgpu_b200.h"
+
+static int launcher_rank(void) {
+  const char* names[] = {"OMPI_COMM_WORLD_RANK", "PMI_RANK", "PMIX_RANK", "MV2_COMM_WORLD_RANK", "SLURM_PROCID"};
+  size_t i;
+  for (i = 0; i < sizeof names / sizeof names[0]; i++) {
+    const char* v = getenv(names[i]);
+    if (v && *v) return atoi(v);
+  }
+  return 0;
+}
+
+static void on_projection(int p, int total, double seconds, void* user) {
+  (void)user;
+  if (seconds < 0.0) {
+    if (total != 1) printf("\n\n\n   << Simulating Projection %d of %d >>\n\n\n", p + 1, total);
+  } else
+    printf("       projection %d of %d done in %.3f s\n", p + 1, total, seconds);
+  fflush(stdout);
+}
+
+static int die(mcgpu_ctx* ctx, int rc) {
+  printf("\n\n   !!MC-GPU b200 failure (code %d)!! %s\n\n", rc, mcgpu_last_error(ctx));
+  fflush(stdout);
+  mcgpu_destroy(ctx);
+  return rc;
+}
+
+int main(int argc, char** argv) {
+  struct timespec t0, t1, t2;
+  mcgpu_ctx* ctx;
+  mcgpu_info info;
+  time_t now = time(NULL);
+  double t_init, t_total;
+  int rc;
+
+  if (launcher_rank() != 0) return 0;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  if (argc != 2) {
+    printf("\n\n   !!read_input!! %s\n\n", argc > 2 ? "Too many input parameters: provide only the input file name." : "Input file name not given as an execution parameter.");
+    return -1;
+  }
+  printf("\n\n     *****************************************************************************\n");
+  printf("     ***   MC-GPU v1.3 command-line compatible engine (mcgpu-b200, sm_100a)      ***\n");
+  printf("     ***   drop-in for the MC-GPU v1.3 x-ray transport code of A. Badal (FDA)    ***\n");
+  printf("     *****************************************************************************\n\n");
+  printf("****** Code execution started on: %s\n\n", ctime(&now));
+  printf("\n             *** CUDA SIMULATION IN THE GPU ***\n");
+  printf("\n    -- INITIALIZATION phase:\n");
+  fflush(stdout);
+
+  ctx = mcgpu_create(NULL, 0); /* every visible device; a .in gpu id that is out of range means the same (Q13) */
+  if (!ctx) {
+    printf("\n\n   !!out of memory creating the context!!\n\n");
+    return -4;
+  }
+  mcgpu_set_verbose(ctx, 1);
+  printf("\n    -- Reading the input file '%s':\n", argv[1]);
+  if ((rc = mcgpu_load_input(ctx, argv[1])) != MCGPU_OK) return die(ctx, rc);
+  if ((rc = mcgpu_load_voxels(ctx, NULL)) != MCGPU_OK) return die(ctx, rc);
+  if ((rc = mcgpu_load_materials(ctx, NULL, 0)) != MCGPU_OK) return die(ctx, rc);
+  mcgpu_get_info(ctx, &info);
+  printf("              x-ray tracks to simulate = %llu\n", info.requested_histories);
+  printf("                   initial random seed = %d\n", info.seed_input);
+  printf("                number of pixels image = %dx%d = %d\n", info.num_pixels_x, info.num_pixels_z, info.num_pixels_x * info.num_pixels_z);
+  printf("                 number of projections = %d\n", info.num_projections);
+  printf("            number of energy bins read = %d\n", info.num_spectrum_bins);
+  printf("                  mean energy spectrum = %.3f keV\n", 0.001f * info.mean_energy_spectrum);
+  printf("       Number of voxels in the input geometry file: %d x %d x %d\n", info.num_voxels_x, info.num_voxels_y, info.num_voxels_z);
+  printf("       Packed voxel layout: %d bits per voxel, %d distinct (material, density) pairs, %d materials in use\n", info.voxel_bits, info.palette_size, info.num_materials_used);
+  printf("       Number of energy values in the mean free path database: %d\n", info.num_energy_values);
+  printf("       ==> CUDA: %d device(s) in use; executing %d blocks of %d threads, %d histories per thread: %llu histories per projection\n", info.num_devices, info.num_blocks,
+         info.threads_per_block, info.histories_per_thread, info.launched_histories);
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  t_init = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+  printf("\n    -- INITIALIZATION finished: elapsed time = %.3f s. \n\n", t_init);
+  printf("\n\n    -- MONTE CARLO LOOP phase.\n\n");
+  fflush(stdout);
+
+  if (info.num_devices < 1) return die(ctx, MCGPU_E_CUDA);
+  if ((rc = mcgpu_run_all(ctx, on_projection, NULL)) != MCGPU_OK) return die(ctx, rc);
+
+  clock_gettime(CLOCK_MONOTONIC, &t2);
+  t_total = (t2.tv_sec - t0.tv_sec) + 1e-9 * (t2.tv_nsec - t0.tv_nsec);
+  mcgpu_get_info(ctx, &info);
+  printf("\n\n\n    -- SIMULATION FINISHED!\n");
+  printf("\n\n       ****** TOTAL SIMULATION PERFORMANCE (including initialization and reporting) ******\n\n");
+  printf("          >>> Execution time including initialization, transport and report: %.3f s.\n", t_total);
+  printf("          >>> Time spent in the Monte Carlo transport and reporting: %.3f s.\n", t_total - t_init);
+  printf("          >>> Total number of simulated x rays:  %llu\n", info.launched_histories * (unsigned long long)info.num_projections);
+  if (t_total > 0.000001)
+    printf("          >>> Total speed (including initialization time) [x-rays/s]:  %.2f\n\n", (double)(info.launched_histories * (unsigned long long)info.num_projections) / t_total);
+  now = time(NULL);
+  printf("\n****** Code execution finished on: %s\n\n", ctime(&now));
+  mcgpu_destroy(ctx);
+  return 0;
+}

@@ -1,0 +1,51 @@
+# Builds libmcgpu_b200.so (C host + sm_100a CUDA), the MC-GPU_v1.3.x drop-in executable, the
+# CPU oracle (test infrastructure) and -- when /root/reference is present -- the reference's own
+# binaries under oracle/_ref/ (checker only; see oracle/README.md).
+PKG      := 4d-cbct-mc_b200
+HOSTDIR  := $(PKG)/csrc/host
+CUDADIR  := $(PKG)/csrc/cuda
+BUILD    := build
+LIBDIR   := $(PKG)/lib
+BINDIR   := $(PKG)/bin
+
+CC       ?= gcc
+NVCC     ?= nvcc
+# -ffp-contract=off: the table builders must round exactly like the reference's host code
+CFLAGS   := -std=gnu11 -O2 -g -fPIC -Wall -Wextra -Wno-unused-result -ffp-contract=off -Iinclude -I$(HOSTDIR)
+# -fmad=false and no fast-math: bit-exact tallies against the reference CUDA source
+NVFLAGS  := -std=c++17 -O3 -lineinfo -fmad=false -gencode arch=compute_100a,code=sm_100a \
+            -Xcompiler -fPIC -Iinclude -I$(HOSTDIR) -Xptxas -v
+
+HOST_SRC := input.c geometry.c voxels.c tables.c ranecu_host.c report.c api.c
+HOST_OBJ := $(HOST_SRC:%.c=$(BUILD)/%.o)
+CUDA_OBJ := $(BUILD)/device.o
+
+all: lib exe oracle
+
+lib: $(LIBDIR)/libmcgpu_b200.so
+exe: $(BINDIR)/MC-GPU_v1.3.x
+oracle:
+	$(MAKE) -C oracle
+
+$(BUILD)/%.o: $(HOSTDIR)/%.c $(HOSTDIR)/mcgpu_host.h include/mcgpu_b200.h
+	@mkdir -p $(BUILD)
+	$(CC) $(CFLAGS) -c $< -o $@
+
+$(BUILD)/device.o: $(CUDADIR)/device.cu $(CUDADIR)/transport.cuh $(HOSTDIR)/mcgpu_host.h
+	@mkdir -p $(BUILD)
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(BUILD)/ptxas_device.log || (cat $(BUILD)/ptxas_device.log; false)
+	@grep -E "registers|spill" $(BUILD)/ptxas_device.log | sort | uniq -c | head -20
+
+$(LIBDIR)/libmcgpu_b200.so: $(HOST_OBJ) $(CUDA_OBJ)
+	@mkdir -p $(LIBDIR)
+	$(NVCC) -shared -o $@ $^ -lz -lpthread -lm -Xlinker -soname=libmcgpu_b200.so
+
+$(BINDIR)/MC-GPU_v1.3.x: $(HOSTDIR)/main.c $(LIBDIR)/libmcgpu_b200.so
+	@mkdir -p $(BINDIR)
+	$(CC) $(CFLAGS) -fPIE $< -o $@ -L$(LIBDIR) -lmcgpu_b200 -Wl,-rpath,'$$ORIGIN/../lib'
+
+clean:
+	rm -rf $(BUILD) $(LIBDIR) $(BINDIR)
+	$(MAKE) -C oracle clean
+
+.PHONY: all lib exe oracle clean
