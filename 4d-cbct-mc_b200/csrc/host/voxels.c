@@ -149,7 +149,7 @@ int mcgpu_finish_volume(mcgpu_ctx* ctx) {
   uint16_t* idx = (uint16_t*)malloc(sizeof(uint16_t) * n);
   uint64_t* pal = (uint64_t*)malloc(sizeof(uint64_t) * MAXPAL);
   uint64_t last_key = ~0ull;
-  int last_val = -1, npal = 0, overflow = 0, k;
+  int last_val = -1, npal = 0, overflow = 0, k, min_bits = 0;
   size_t i;
   if (!keys || !vals || !idx || !pal) {
     free(keys), free(vals), free(idx), free(pal);
@@ -185,6 +185,11 @@ int mcgpu_finish_volume(mcgpu_ctx* ctx) {
   }
   free(v->palette_density), free(v->palette_material), free(v->packed);
   v->palette_density = NULL, v->palette_material = NULL, v->packed = NULL;
+  { /* MCGPU_VOXEL_BITS=8|16|64 forces a wider packing than needed (parity tests of every kernel variant) */
+    const char* force = getenv("MCGPU_VOXEL_BITS");
+    min_bits = force ? atoi(force) : 0;
+    if (min_bits >= 64) overflow = 1;
+  }
   if (overflow) {
     mcgpu_f2* p = (mcgpu_f2*)malloc(sizeof(mcgpu_f2) * n);
     if (!p) {
@@ -210,13 +215,13 @@ int mcgpu_finish_volume(mcgpu_ctx* ctx) {
       memcpy(&v->palette_density[k], &bits, 4);
       v->palette_material[k] = (uint8_t)(pal[k] >> 32);
     }
-    if (npal <= 16) {
+    if (npal <= 16 && min_bits <= 4) {
       uint8_t* p = (uint8_t*)calloc((n + 1) / 2, 1);
       for (i = 0; i < n; i++) p[i >> 1] |= (uint8_t)(idx[i] << ((i & 1) * 4));
       v->packed = p;
       v->packed_bytes = (n + 1) / 2;
       v->voxel_bits = 4;
-    } else if (npal <= 256) {
+    } else if (npal <= 256 && min_bits <= 8) {
       uint8_t* p = (uint8_t*)malloc(n);
       for (i = 0; i < n; i++) p[i] = (uint8_t)idx[i];
       v->packed = p;

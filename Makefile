@@ -38,7 +38,7 @@ $(BUILD)/device.o: $(CUDADIR)/device.cu $(CUDADIR)/transport.cuh $(HOSTDIR)/mcgp
 
 $(LIBDIR)/libmcgpu_b200.so: $(HOST_OBJ) $(CUDA_OBJ)
 	@mkdir -p $(LIBDIR)
-	$(NVCC) -shared -o $@ $^ -lz -lpthread -lm -Xlinker -soname=libmcgpu_b200.so
+	$(NVCC) -shared -gencode arch=compute_100a,code=sm_100a -o $@ $^ -lz -lpthread -lm -Xlinker -soname=libmcgpu_b200.so
 
 $(BINDIR)/MC-GPU_v1.3.x: $(HOSTDIR)/main.c $(LIBDIR)/libmcgpu_b200.so
 	@mkdir -p $(BINDIR)

@@ -136,7 +136,8 @@ int mcgpu_projection_seed(mcgpu_ctx* ctx, int p, int* seed_out);
  *   "rayleigh_pmax" float[nE*25]     (H:2304, 2381-2394)
  *   "compton_fco|uico|fj0" float[25*40], "compton_noscco" int[25] (H:2415-2426)
  *   "espc","espc_cutoff" float[256], "espc_alias" int16[256]      (H:3498-3587)
- *   "source" / "detector": packed float records per projection, see csrc/host/mcgpu_host.h
+ *   "views": mcgpu_view records (source + detector pose) per projection, see csrc/host/mcgpu_host.h
+ *   "voxel_material" uint8[Nvox], "voxel_density" float[Nvox], "voxel_packed" (device layout)
  *   "density_max" float[25]          (H:2132)
  * Returns bytes copied (<= cap) or a negative error; out==NULL returns the size. */
 long long mcgpu_copy_table(const mcgpu_ctx* ctx, const char* name, void* out, size_t cap);

@@ -1,0 +1,151 @@
+"""Voxel-file ingest (text, gzip, in-memory), palette packing, and their error behaviour
+(reference: load_voxels, MC-GPU_v1.3.cu:1996-2145)."""
+import gzip
+
+import numpy as np
+import pytest
+
+
+def unpack(packed, bits, n):
+    if bits == 4:
+        b = packed[: (n + 1) // 2]
+        out = np.empty(2 * len(b), dtype=np.uint8)
+        out[0::2] = b & 15
+        out[1::2] = b >> 4
+        return out[:n].astype(np.int64)
+    if bits == 8:
+        return packed[:n].astype(np.int64)
+    if bits == 16:
+        return packed.view(np.uint16)[:n].astype(np.int64)
+    raise AssertionError(bits)
+
+
+def load(pkg, inp, **kw):
+    eng = pkg.engine.Engine()
+    eng.load_input(inp)
+    return eng
+
+
+def test_vox_gz_plain_and_memory_agree(pkg, cases, tmp_path):
+    from conftest import build_case
+
+    inp_gz, cfg, ph = cases["thorax_p4"]
+    inp_txt, _, _ = build_case(pkg, "thorax_p4", tmp_path / "plain", compressed=False)
+    with load(pkg, inp_gz) as a, load(pkg, inp_txt) as b, load(pkg, inp_gz) as c:
+        a.load_voxels()
+        b.load_voxels()
+        c.set_voxels(ph.materials, ph.densities, ph.spacing_cm)
+        for t in ("voxel_material", "voxel_density", "voxel_packed", "density_max"):
+            assert np.array_equal(a.table(t), b.table(t)), t
+        # the text file carries %.6f densities; in-memory ones are the float32 originals
+        assert np.array_equal(a.table("voxel_material"), c.table("voxel_material"))
+        assert np.allclose(a.table("voxel_density"), c.table("voxel_density"), atol=5e-7)
+        mat = a.table("voxel_material").reshape(ph.shape[::-1])  # z, y, x
+        assert np.array_equal(mat, ph.materials.transpose(2, 1, 0))
+        i = a.info
+        assert (i.num_voxels_x, i.num_voxels_y, i.num_voxels_z) == ph.shape
+
+
+@pytest.mark.parametrize("n_pairs,bits", [(3, 4), (16, 4), (17, 8), (256, 8), (257, 16), (5000, 16), (70000, 64)])
+def test_palette_packing_round_trips(pkg, cases, n_pairs, bits):
+    inp, _, _ = cases["water_p1"]
+    rng = np.random.default_rng(n_pairs)
+    shape = (41, 37, 53)  # odd sizes: exercises the nibble tail
+    n = int(np.prod(shape))
+    pair = rng.integers(0, n_pairs, size=n)
+    pair[:n_pairs] = np.arange(n_pairs)  # every pair occurs
+    mats = (pair % 22 + 1).astype(np.uint8).reshape(shape[::-1]).transpose(2, 1, 0)
+    dens = (0.001 + (pair // 22 + 1) * 1e-4 + (pair % 22) * 0.05).astype(np.float32).reshape(shape[::-1]).transpose(2, 1, 0)
+    with load(pkg, inp) as eng:
+        eng.set_voxels(mats, dens, (0.1, 0.2, 0.3))
+        info = eng.info
+        assert info.voxel_bits == bits
+        m = eng.table("voxel_material").astype(np.int64)
+        d = eng.table("voxel_density")
+        assert np.array_equal(m, mats.transpose(2, 1, 0).reshape(-1))
+        assert np.array_equal(d, dens.transpose(2, 1, 0).reshape(-1))
+        if bits != 64:
+            assert info.palette_size == n_pairs
+            idx = unpack(eng.table("voxel_packed"), bits, n)
+            assert idx.max() == n_pairs - 1
+            # same index <=> same (material, density) pair
+            key = m * (1 << 32) + d.view(np.uint32).astype(np.int64)
+            first = {}
+            for i, k in zip(idx[:20000], key[:20000]):
+                assert first.setdefault(int(i), int(k)) == int(k)
+        dmax = eng.table("density_max")
+        for mat in range(1, 23):
+            sel = m == mat
+            assert dmax[mat - 1] == (d[sel].max() if sel.any() else np.float32(-999.0))
+
+
+def write_tiny_vox(path, body, n=(2, 1, 1)):
+    text = f"[SECTION VOXELS HEADER v.2008-04-13]\n{n[0]} {n[1]} {n[2]}\n1.0 1.0 1.0\n[END OF VXH SECTION]\n" + body
+    if str(path).endswith(".gz"):
+        with gzip.open(path, "wt") as f:
+            f.write(text)
+    else:
+        path.write_text(text)
+
+
+@pytest.mark.parametrize("body,msg", [
+    ("0 1.0\n1 1.0\n", "out of range"),        # material 0 (H:2120)
+    ("26 1.0\n1 1.0\n", "out of range"),       # material > MAX_MATERIALS (H:2115)
+    ("1 0.0\n1 1.0\n", "density"),             # density below 1e-9 (H:2126)
+    ("1 1.0\n", "premature end"),              # ragged: fewer voxels than the header promises
+    ("1 1.0\nxx yy\n", "expecting material"),  # garbage line
+])
+def test_bad_voxel_files_are_rejected(pkg, cases, tmp_path, body, msg):
+    inp, _, _ = cases["water_p1"]
+    vox = tmp_path / "bad.vox"
+    write_tiny_vox(vox, body)
+    with load(pkg, inp) as eng:
+        with pytest.raises(pkg.engine.McgpuError) as e:
+            eng.load_voxels(vox)
+        assert e.value.code == -2 and msg in str(e.value)
+
+
+def test_blank_and_comment_lines_are_skipped_like_the_reference(pkg, cases, tmp_path):
+    inp, _, _ = cases["water_p1"]
+    vox = tmp_path / "ok.vox.gz"
+    write_tiny_vox(vox, "\n# comment\n1 0.001300\n\n\n 6 1.000000\n\n", n=(2, 1, 1))
+    with load(pkg, inp) as eng:
+        eng.load_voxels(vox)
+        assert list(eng.table("voxel_material")) == [1, 6]
+        assert list(eng.table("voxel_density")) == [np.float32(0.0013), np.float32(1.0)]
+        assert eng.info.voxel_bits == 4 and eng.info.palette_size == 2
+
+
+def test_missing_files(pkg, cases, tmp_path):
+    inp, _, _ = cases["water_p1"]
+    with load(pkg, inp) as eng:
+        with pytest.raises(pkg.engine.McgpuError):
+            eng.load_voxels(tmp_path / "nope.vox")
+        eng.load_voxels()
+        with pytest.raises(pkg.engine.McgpuError) as e:
+            eng.load_materials([tmp_path / "nope.mcgpu"])
+        assert e.value.code == -2
+
+
+def test_material_used_by_voxels_but_not_listed_is_an_error(pkg, cases):
+    inp, _, _ = cases["thorax_p4"]
+    with load(pkg, inp) as eng:
+        eng.load_voxels()
+        with pytest.raises(pkg.engine.McgpuError) as e:
+            eng.load_materials(pkg.mcio.material_paths()[:3])
+        assert "has no material file" in str(e.value)
+
+
+def test_spectrum_outside_table_range_is_rejected(pkg, cases, tmp_path):
+    inp, _, _ = cases["water_p1"]
+    spc = tmp_path / "hot.spc"
+    spc.write_text("100.0e3 1.0\n150.0e3 1.0\n200.0e3 -1\n")
+    text = open(inp).read()
+    old = [line for line in text.splitlines() if "X-RAY ENERGY SPECTRUM FILE" in line][0]
+    f = tmp_path / "hot.in"
+    f.write_text(text.replace(old, f"{spc}  # X-RAY ENERGY SPECTRUM FILE"))
+    with pkg.engine.Engine() as eng:
+        eng.load_input(f).load_voxels()
+        with pytest.raises(pkg.engine.McgpuError) as e:
+            eng.load_materials()
+        assert e.value.code == -1 and "outside the tabulated energy interval" in str(e.value)
