@@ -6,6 +6,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <stdlib.h>
+
+#include "regroup.cuh"
 #include "transport.cuh"
 
 using namespace mcgpu;
@@ -38,6 +41,9 @@ struct mcgpu_device {
   mcgpu_spectrum* d_spectrum;
   unsigned long long* d_image;
   unsigned long long* d_peer_stage;  // used when peer access is unavailable
+  unsigned long long* d_stream_counter;  // next stream of the running launch (regrouping kernel)
+  int kernel_generation;                 // 2 = regrouping persistent warps (default), 1 = one thread per stream
+  int w_threshold;
   uint64_t* h_stage;
   int timed;
 };
@@ -180,7 +186,8 @@ extern "C" struct mcgpu_device* mcgpu_dev_open(int ordinal, char* err, size_t er
 static void free_scene_allocs(mcgpu_device* d) {
   cudaFree(d->d_volume), cudaFree(d->d_palette), cudaFree(d->d_mfp), cudaFree(d->d_woodcock);
   cudaFree(d->d_ray_xpab), cudaFree(d->d_ray_itl_itu), cudaFree(d->d_cmp_shells), cudaFree(d->d_spectrum);
-  cudaFree(d->d_image), cudaFree(d->d_peer_stage);
+  cudaFree(d->d_image), cudaFree(d->d_peer_stage), cudaFree(d->d_stream_counter);
+  d->d_stream_counter = NULL;
   if (d->h_stage) cudaFreeHost(d->h_stage);
   d->d_volume = NULL, d->d_palette = NULL, d->d_mfp = NULL, d->d_woodcock = NULL, d->d_ray_xpab = NULL;
   d->d_ray_itl_itu = NULL, d->d_cmp_shells = NULL, d->d_spectrum = NULL, d->d_image = NULL, d->d_peer_stage = NULL, d->h_stage = NULL;
@@ -223,6 +230,15 @@ extern "C" int mcgpu_dev_upload(struct mcgpu_device* d, const mcgpu_scene* s, co
   d->image_words = (size_t)4 * npix_total;
   if (upload(&d->d_image, NULL, sizeof(unsigned long long) * d->image_words, err, errlen)) return -1;
   CK(cudaMemset(d->d_image, 0, sizeof(unsigned long long) * d->image_words));
+  CK(cudaMalloc((void**)&d->d_stream_counter, sizeof(unsigned long long)));
+  {  // tuning / A-B switches (documented in DESIGN.md); the defaults are the product path
+    const char* k = getenv("MCGPU_KERNEL");
+    const char* t = getenv("MCGPU_W_THRESHOLD");
+    d->kernel_generation = (k && atoi(k) == 1) ? 1 : 2;
+    d->w_threshold = t ? atoi(t) : 12;
+    if (d->w_threshold < 1) d->w_threshold = 1;
+    if (d->w_threshold > 32) d->w_threshold = 32;
+  }
 
   SceneDev& sc = d->scene;
   memset(&sc, 0, sizeof sc);
@@ -277,10 +293,19 @@ extern "C" int mcgpu_dev_launch(struct mcgpu_device* d, const mcgpu_view* view, 
     size_t smem = ((sizeof(SharedTables) + 15) & ~size_t(15)) + sizeof(float4) * d->scene.num_slots * MCGPU_MAX_SHELLS;
     if (d->voxel_bits == 4 || d->voxel_bits == 8) smem += sizeof(float2) * d->scene.palette_size;
 #define LAUNCH(B)                                                                                                                        \
-  {                                                                                                                                      \
+  if (d->kernel_generation == 1) {                                                                                                       \
     CK(cudaFuncSetAttribute(transport_streams<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                              \
     transport_streams<B><<<(unsigned)grid, block, smem, d->stream>>>(d->scene, *view, l->stream_begin, l->stream_end, l->histories_per_thread, \
                                                                      l->seed_input, g1, g2);                                            \
+  } else {                                                                                                                               \
+    int per_sm = 0;                                                                                                                      \
+    CK(cudaFuncSetAttribute(transport_regroup<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                              \
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, transport_regroup<B>, block, smem));                                       \
+    long long pgrid = (long long)d->sm_count * (per_sm > 0 ? per_sm : 1);                                                                \
+    if (pgrid > grid) pgrid = grid;                                                                                                      \
+    CK(cudaMemsetAsync(d->d_stream_counter, 0, sizeof(unsigned long long), d->stream));                                                  \
+    transport_regroup<B><<<(unsigned)pgrid, block, smem, d->stream>>>(d->scene, *view, l->stream_begin, l->stream_end, l->histories_per_thread, \
+                                                                      l->seed_input, g1, g2, d->d_stream_counter, d->w_threshold);      \
   }
     switch (d->voxel_bits) {
       case 4: LAUNCH(4) break;

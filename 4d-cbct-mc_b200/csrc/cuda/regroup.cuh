@@ -1,0 +1,172 @@
+// Transport kernel, generation 2: persistent warps that regroup photons by event.
+//
+// Why: the reference's structure (one thread = one stream, nested variable-length loops:
+// histories > interactions > delta-tracking steps, rejection loops inside Compton) leaves, on
+// B200, 2.3 of 32 lanes active per issued warp instruction (ncu: smsp__thread_inst_executed_per_
+// inst_executed = 2.31, profiles/r01_v1_*): every nesting level multiplies the divergence loss,
+// while the issue slots are ~80 % busy issuing mostly-empty instructions.
+//
+// How: each lane still owns one RANECU stream and runs that stream's histories strictly in order
+// (so every float of every trajectory, and therefore every integer tally, is unchanged), but the
+// nested loops are flattened into a per-lane state machine and the warp executes one EVENT TYPE at
+// a time for all lanes that are waiting for it:
+//   W  delta-tracking step (the dominant unit, ~100 instructions)   -> W | C | R | T | N
+//   C  Compton interaction                                           -> W | N
+//   R  Rayleigh interaction                                          -> W
+//   T  tally on the detector                                         -> N
+//   N  next history of the stream (source sampling)                  -> W | T | I
+//   I  next stream from the global counter (RANECU jump-ahead)       -> N | F(inished)
+// Lanes that leave W wait (masked) while the rest keep stepping; when fewer than `w_threshold`
+// lanes are still in W the pending events are executed type by type, which turns (almost) all
+// lanes back to W.  Streams are handed out dynamically (warp-aggregated atomic on a global
+// counter), so the grid is persistent: SM count x resident CTAs, and finished lanes refill.
+#pragma once
+#include "transport.cuh"
+
+namespace mcgpu {
+
+enum LaneState : int { ST_W = 0, ST_C = 1, ST_R = 2, ST_T = 3, ST_N = 4, ST_I = 5, ST_F = 6 };
+
+#define MCGPU_FULL_MASK 0xffffffffu
+
+template <int BITS>
+__global__ void __launch_bounds__(128, 8) transport_regroup(const SceneDev sc, const __grid_constant__ mcgpu_view vw, long long stream_begin, long long stream_end,
+                                                            int histories_per_thread, int seed_input, int g1, int g2, unsigned long long* __restrict__ stream_counter,
+                                                            int w_threshold) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SharedTables& st = *reinterpret_cast<SharedTables*>(smem_raw);
+  float4* sh_shells = reinterpret_cast<float4*>(smem_raw + ((sizeof(SharedTables) + 15) & ~size_t(15)));
+  float2* sh_palette = reinterpret_cast<float2*>(sh_shells + sc.num_slots * MCGPU_MAX_SHELLS);
+
+  for (int i = threadIdx.x; i < MCGPU_MAX_ENERGY_BINS; i += blockDim.x) {
+    st.espc[i] = sc.spectrum->espc[i];
+    st.cutoff[i] = sc.spectrum->cutoff[i];
+    st.alias[i] = sc.spectrum->alias[i];
+  }
+  if (threadIdx.x == 0) st.num_bins = sc.spectrum->num_bins;
+  for (int i = threadIdx.x; i < sc.num_slots * MCGPU_MAX_SHELLS; i += blockDim.x) sh_shells[i] = sc.cmp_shells[i];
+  if (BITS == 4 || BITS == 8)
+    for (int i = threadIdx.x; i < sc.palette_size; i += blockDim.x) sh_palette[i] = sc.palette[i];
+  __syncthreads();
+
+  const unsigned lane = threadIdx.x & 31u;
+  const long long n_streams = stream_end - stream_begin;
+
+  // per-lane photon / stream state (registers)
+  Photon p;
+  Ranecu rng;
+  RnLocal rn;
+  mcgpu_mfp_record rec;
+  float mfp_woodcock = 0.f, mfp_density = 0.f;
+  int index = 0, slot = 0, slot_old = -1, scatter_state = 0, hist_left = 0;
+  int state = ST_I;
+  p.x = p.y = p.z = p.u = p.v = p.w = p.E = 0.f;
+  rng.s1 = rng.s2 = 1;
+  rec.ax = rec.ay = rec.az = rec.bx = rec.by = rec.bz = rec.pmax_next = rec.pad = 0.f;
+
+  for (;;) {
+    const unsigned m_w = __ballot_sync(MCGPU_FULL_MASK, state == ST_W);
+    const unsigned m_f = __ballot_sync(MCGPU_FULL_MASK, state == ST_F);
+    if (m_f == MCGPU_FULL_MASK) break;
+    const int n_w = __popc(m_w);
+    const int n_pending = 32 - n_w - __popc(m_f);
+
+    if (n_w >= w_threshold || n_pending == 0) {
+      // ---------------------------------------------------------------- W: one delta-tracking step (K:249-279)
+      if (state == ST_W) {
+        const float step = -(mfp_woodcock)*logf(rng.uniform());
+        p.x += step * p.u;
+        p.y += step * p.v;
+        p.z += step * p.w;
+        const int absvox = locate_voxel(sc, p);
+        if (absvox < 0) {
+          state = ST_T;  // escaped with index > -1: goes to the detector
+        } else {
+          const float2 md = fetch_voxel<BITS>(sc, sh_palette, absvox);
+          slot = __float_as_int(md.y);
+          if (slot != slot_old) {
+            const float4* r4 = reinterpret_cast<const float4*>(&sc.mfp[(size_t)index * sc.num_slots + slot]);
+            const float4 lo = __ldg(r4), hi = __ldg(r4 + 1);
+            rec.ax = lo.x, rec.ay = lo.y, rec.az = lo.z, rec.bx = lo.w;
+            rec.by = hi.x, rec.bz = hi.y, rec.pmax_next = hi.z;
+            slot_old = slot;
+          }
+          mfp_density = mfp_woodcock * md.x;
+          float prob = 1.0f - mfp_density * (rec.ax + p.E * rec.bx);
+          const float randno = rng.uniform();
+          if (!(randno < prob)) {  // real interaction: classify now (K:289-353), sample later with the other lanes
+            prob += mfp_density * (rec.ay + p.E * rec.by);
+            if (randno < prob) {
+              state = ST_C;
+            } else {
+              prob += mfp_density * (rec.az + p.E * rec.bz);
+              state = (randno < prob) ? ST_R : ST_N;  // else: photoelectric absorption, history over
+            }
+          }
+        }
+      }
+    } else {
+      // ---------------------------------------------------------------- T: detector tally (K:377-381)
+      if (state == ST_T) {
+        tally_photon(sc, vw, p, scatter_state);
+        state = ST_N;
+      }
+      // ---------------------------------------------------------------- I: next stream of the launch (K:198)
+      {
+        const bool want = (state == ST_N && hist_left == 0) || state == ST_I;
+        const unsigned m_i = __ballot_sync(MCGPU_FULL_MASK, want);
+        if (m_i) {
+          unsigned long long base = 0;
+          const int leader = __ffs(m_i) - 1;
+          if ((int)lane == leader) base = atomicAdd(stream_counter, (unsigned long long)__popc(m_i));
+          base = __shfl_sync(MCGPU_FULL_MASK, base, leader);
+          if (want) {
+            const long long s = (long long)base + __popc(m_i & ((1u << lane) - 1u));
+            if (s < n_streams) {
+              ranecu_init(rng, stream_begin + s, seed_input, g1, g2);
+              hist_left = histories_per_thread;
+              state = ST_N;
+            } else {
+              state = ST_F;
+            }
+          }
+        }
+      }
+      // ---------------------------------------------------------------- N: next history (K:210-234)
+      if (state == ST_N) {
+        hist_left--;
+        const bool enters = emit_photon(sc, vw, st, rng, p);
+        scatter_state = 0;
+        index = __float2int_rd((p.E - sc.e0) * sc.ide);
+        const float2 w = __ldg(&sc.woodcock[index]);
+        mfp_woodcock = w.x + p.E * w.y;
+        slot_old = -1;
+        state = enters ? ST_W : ST_T;  // a primary that misses the voxels can still hit the detector (K:240-241)
+      }
+      // ---------------------------------------------------------------- C: Compton (K:290-326)
+      if (state == ST_C) {
+        const double costh = sample_compton(p.E, sh_shells + slot * MCGPU_MAX_SHELLS, sc.cmp_noscco[slot], rng, rn);
+        deflect(p, costh, 6.28318530717958647693 * rng.uniform_d());
+        index = __float2int_rd((p.E - sc.e0) * sc.ide);
+        if (index > -1) {
+          const float2 w = __ldg(&sc.woodcock[index]);
+          mfp_woodcock = w.x + p.E * w.y;
+          slot_old = -2;
+          scatter_state = (scatter_state == 0) ? 1 : 3;
+          state = ST_W;
+        } else {
+          state = ST_N;  // below the tabulated energies: absorbed (K:311, K:372)
+        }
+      }
+      // ---------------------------------------------------------------- R: Rayleigh (K:329-347)
+      if (state == ST_R) {
+        const double costh = sample_rayleigh(sc, p.E, slot, rec.pmax_next, rng);
+        deflect(p, costh, 6.28318530717958647693 * rng.uniform_d());
+        scatter_state = (scatter_state == 0) ? 2 : 3;
+        state = ST_W;
+      }
+    }
+  }
+}
+
+}  // namespace mcgpu

@@ -89,6 +89,11 @@ int mcgpu_parse_input(mcgpu_ctx* ctx, const char* in_path) {
   d = 0.0;
   sscanf(line, "%lf", &d);
   in->total_histories = (unsigned long long)(d + 0.0001);
+  /* H:654: values below 95 000 mean "simulate this many SECONDS" (speed test + extrapolation), a mode
+   * that is irreproducible by construction and that cbctmc never uses (it always writes a history count). */
+  if (in->total_histories < 95000ull)
+    BAIL("read_input: %llu is below 95000 and would mean a simulation TIME in seconds in MC-GPU; time-limited runs are not supported, give a number of histories",
+         in->total_histories);
   mcgpu_fgets_trimmed(line, MCGPU_LINE, f);
   sscanf(line, "%d", &in->seed_input);
   mcgpu_fgets_trimmed(line, MCGPU_LINE, f);

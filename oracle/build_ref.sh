@@ -14,6 +14,9 @@ up_to_date "$OUT/MC-GPU_v1.3_CPU.x" || gcc -x c -O3 -fgnu89-inline "$SRC/MC-GPU_
 if command -v nvcc >/dev/null 2>&1; then
   COMMON="-m64 -O3 -DUSING_CUDA -I$SRC -I$REF/docker/cuda-samples/Common -lz -gencode=arch=compute_100,code=sm_100 -Wno-deprecated-gpu-targets -w"
   up_to_date "$OUT/MC-GPU_v1.3_sm100_exact.x" || nvcc "$SRC/MC-GPU_v1.3.cu" -o "$OUT/MC-GPU_v1.3_sm100_exact.x" $COMMON -fmad=false
+  # the reference's own host stages (read_input ... load_material), nvcc/C++ host semantics, dumped as raw bytes
+  HERE=$(cd "$(dirname "$0")" && pwd)
+  up_to_date "$OUT/ref_host_dump.x" || nvcc "$HERE/ref_host_dump.cu" -o "$OUT/ref_host_dump.x" $COMMON
   up_to_date "$OUT/MC-GPU_v1.3_sm100_fast.x" || nvcc "$SRC/MC-GPU_v1.3.cu" -o "$OUT/MC-GPU_v1.3_sm100_fast.x" $COMMON -use_fast_math
 fi
 ls -la "$OUT"

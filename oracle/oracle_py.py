@@ -13,6 +13,7 @@ REF_DIR = HERE / "_ref"
 REF_CPU = REF_DIR / "MC-GPU_v1.3_CPU.x"
 REF_CUDA_EXACT = REF_DIR / "MC-GPU_v1.3_sm100_exact.x"
 REF_CUDA_FAST = REF_DIR / "MC-GPU_v1.3_sm100_fast.x"
+REF_HOST_DUMP = REF_DIR / "ref_host_dump.x"
 
 _lib = None
 
@@ -139,3 +140,19 @@ def run_reference_binary(binary: Path, in_path: Path, cwd: Path | None = None, t
     if res.returncode != 0:
         raise RuntimeError(f"{binary.name} exited {res.returncode}:\n{res.stdout[-2000:]}\n{res.stderr[-2000:]}")
     return res.stdout
+
+
+def reference_host_dump(in_path: Path, out_path: Path) -> dict:
+    """Run the reference's OWN host stages (oracle/ref_host_dump.cu: read_input, spectrum, CT
+    trajectory, load_voxels, load_material; nvcc host semantics) and return the raw tables."""
+    import struct
+
+    subprocess.run([str(REF_HOST_DUMP), str(in_path), str(out_path)], check=True, capture_output=True, timeout=600)
+    blob = Path(out_path).read_bytes()
+    out, i = {}, 0
+    while i < len(blob):
+        tag = blob[i:i + 32].split(b"\0")[0].decode()
+        (n,) = struct.unpack("<Q", blob[i + 32:i + 40])
+        out[tag] = blob[i + 40:i + 40 + n]
+        i += 40 + n
+    return out

@@ -101,3 +101,14 @@ def test_executable_tolerates_mpirun_style_launch(pkg, cases):
     env = dict(os.environ, OMPI_COMM_WORLD_RANK="1")
     res = subprocess.run([str(exe), str(cases["water_p1"][0])], capture_output=True, text=True, env=env)
     assert res.returncode == 0 and res.stdout == ""
+
+
+def test_time_limited_mode_is_rejected(pkg, cases, tmp_path):
+    """MC-GPU reads a history count below 95 000 as seconds (H:654); cbctmc never uses that mode."""
+    text = Path(cases["water_p1"][0]).read_text().replace("200000  # TOTAL NUMBER", "600  # TOTAL NUMBER")
+    f = tmp_path / "time.in"
+    f.write_text(text)
+    with pkg.engine.Engine() as eng:
+        with pytest.raises(pkg.engine.McgpuError) as e:
+            eng.load_input(f)
+        assert e.value.code == -2 and "seconds" in str(e.value)

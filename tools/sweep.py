@@ -1,0 +1,64 @@
+#!/usr/bin/env python3
+"""Kernel A/B and tuning sweep on the GPU box: histories/s of one projection for each workload and
+each (MCGPU_KERNEL, MCGPU_W_THRESHOLD) setting; every variant is also checked for bit-identical
+tallies against the first one.  Usage: python tools/sweep.py [workloads...] [--hist N] [--thresholds a,b,c]"""
+import json
+import os
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+from __graft_entry__ import import_package  # noqa: E402
+
+pkg = import_package()
+
+
+def main():
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    opts = dict(a[2:].split("=") for a in sys.argv[1:] if a.startswith("--") and "=" in a)
+    hist = int(opts.get("hist", 100_000_000))
+    thresholds = [int(x) for x in opts.get("thresholds", "4,8,12,16,20,24").split(",")]
+    kernels = [int(x) for x in opts.get("kernels", "1,2").split(",")]
+    workloads = args or ["thorax", "catphan"]
+    factories = {"thorax": pkg.phantoms.thorax, "catphan": pkg.phantoms.catphan604, "water": pkg.phantoms.water_cylinder,
+                 "air": pkg.phantoms.air_scan, "linepairs": pkg.phantoms.line_pairs}
+    out = {}
+    for wl in workloads:
+        ph = factories[wl]()
+        tmp = Path(tempfile.mkdtemp())
+        cfg = pkg.mcio.ScanConfig(n_histories=hist, n_projections=1 if wl == "air" else 894, source_position=pkg.mcio.default_source_position(ph.size_mm))
+        inp = pkg.mcio.write_input(cfg, tmp / "x.vox", tmp, tmp / "input.in")
+        base = None
+        configs = [(k, t) for k in kernels for t in (thresholds if k == 2 else [0])]
+        for k, t in configs:
+            os.environ["MCGPU_KERNEL"] = str(k)
+            os.environ["MCGPU_W_THRESHOLD"] = str(t)
+            eng = pkg.engine.Engine([0])
+            eng.load_input(inp).set_voxels(ph.materials, ph.densities, ph.spacing_cm).load_materials()
+            info = eng.info
+            n = info.num_blocks * info.threads_per_block
+            p = 0 if wl == "air" else 100
+            eng.run_streams(p, 0, n, fetch=False)  # warm-up
+            ms = []
+            for _ in range(2):
+                eng.run_streams(p, 0, n, fetch=False)
+                ms.append(eng.last_kernel_ms)
+            img = eng.run_projection(p)
+            same = True if base is None else bool(np.array_equal(img, base))
+            if base is None:
+                base = img
+            rate = info.launched_histories / (min(ms) / 1e3)
+            out[f"{wl}/k{k}/t{t}"] = {"hist_per_s": rate, "ms": min(ms), "identical_to_first": same}
+            print(f"{wl:10s} kernel v{k} thresh {t:2d}: {rate:.4g} hist/s ({min(ms):.1f} ms) identical={same}", flush=True)
+            eng.close()
+    (ROOT / "gpurun_out").mkdir(exist_ok=True)
+    (ROOT / "gpurun_out" / "sweep.json").write_text(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main()
