@@ -255,6 +255,9 @@ extern "C" int mcgpu_dev_upload(struct mcgpu_device* d, const mcgpu_scene* s, co
   sc.num_slots = s->num_slots;
   sc.palette_size = s->palette_size;
   sc.num_values = s->num_values;
+  sc.max_shells = 1;
+  for (int k = 0; k < s->num_slots; k++)
+    if (s->cmp_noscco[k] > sc.max_shells) sc.max_shells = s->cmp_noscco[k];
   sc.nvx = v->nx, sc.nvy = v->ny, sc.nvz = v->nz;
   for (int k = 0; k < 3; k++) {
     sc.inv_voxel[k] = v->inv_voxel_size[k];
@@ -299,6 +302,7 @@ extern "C" int mcgpu_dev_launch(struct mcgpu_device* d, const mcgpu_view* view, 
                                                                      l->seed_input, g1, g2);                                            \
   } else {                                                                                                                               \
     int per_sm = 0;                                                                                                                      \
+    smem += sizeof(float) * (MCGPU_REGROUP_BLOCK / 32) * 32 * regroup_scratch_stride(d->scene.max_shells);                               \
     CK(cudaFuncSetAttribute(transport_regroup<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                              \
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, transport_regroup<B>, block, smem));                                       \
     long long pgrid = (long long)d->sm_count * (per_sm > 0 ? per_sm : 1);                                                                \

@@ -1,42 +1,54 @@
 // Transport kernel, generation 2: persistent warps that regroup photons by event.
 //
 // Why: the reference's structure (one thread = one stream, nested variable-length loops:
-// histories > interactions > delta-tracking steps, rejection loops inside Compton) leaves, on
-// B200, 2.3 of 32 lanes active per issued warp instruction (ncu: smsp__thread_inst_executed_per_
-// inst_executed = 2.31, profiles/r01_v1_*): every nesting level multiplies the divergence loss,
-// while the issue slots are ~80 % busy issuing mostly-empty instructions.
+// histories > interactions > delta-tracking steps, rejection loops over up to 34 shells inside
+// Compton) leaves, on B200, 2.3 of 32 lanes active per issued warp instruction (ncu:
+// smsp__thread_inst_executed_per_inst_executed = 2.31, profiles/r01_v1_thorax_ncu_summary.txt):
+// every nesting level multiplies the divergence loss while the issue slots are ~80 % busy issuing
+// mostly-empty instructions.
 //
 // How: each lane still owns one RANECU stream and runs that stream's histories strictly in order
 // (so every float of every trajectory, and therefore every integer tally, is unchanged), but the
 // nested loops are flattened into a per-lane state machine and the warp executes one EVENT TYPE at
 // a time for all lanes that are waiting for it:
-//   W  delta-tracking step (the dominant unit, ~100 instructions)   -> W | C | R | T | N
-//   C  Compton interaction                                           -> W | N
-//   R  Rayleigh interaction                                          -> W
-//   T  tally on the detector                                         -> N
-//   N  next history of the stream (source sampling)                  -> W | T | I
-//   I  next stream from the global counter (RANECU jump-ahead)       -> N | F(inished)
+//   W   delta-tracking step (the dominant unit, ~100 instructions)       -> W | C | R | T | N
+//   C   Compton, fresh: S0 = incoherent scattering function at theta=pi   -> CT
+//   CT  Compton, one tau trial (propose, S(tau), accept/reject)           -> CT | W | N
+//   R   Rayleigh interaction                                              -> W
+//   T   tally on the detector                                             -> N
+//   N   next history of the stream (source sampling)                      -> W | T
+//   I   next stream from the global counter (RANECU jump-ahead)           -> N | F(inished)
 // Lanes that leave W wait (masked) while the rest keep stepping; when fewer than `w_threshold`
 // lanes are still in W the pending events are executed type by type, which turns (almost) all
-// lanes back to W.  Streams are handed out dynamically (warp-aggregated atomic on a global
-// counter), so the grid is persistent: SM count x resident CTAs, and finished lanes refill.
+// lanes back to W.  A rejected Compton trial is not looped on the spot: the lane stays in CT and
+// takes its next trial together with the Compton lanes of the next event phase.  The per-shell
+// terms of the Compton sums (rsqrtf + expf per shell, up to 34 shells for tissue) are evaluated
+// cooperatively by all 32 lanes (coop_shell_terms) and added by the owner lane in shell order, so
+// the heavy part runs on full warps whatever the number of photons in Compton.  Streams are handed
+// out dynamically (warp-aggregated atomic on a global counter): the grid is persistent, SM count x
+// resident CTAs, and finished lanes refill.
 #pragma once
 #include "transport.cuh"
 
 namespace mcgpu {
 
-enum LaneState : int { ST_W = 0, ST_C = 1, ST_R = 2, ST_T = 3, ST_N = 4, ST_I = 5, ST_F = 6 };
+enum LaneState : int { ST_W = 0, ST_C = 1, ST_CT = 2, ST_R = 3, ST_T = 4, ST_N = 5, ST_I = 6, ST_F = 7 };
 
 #define MCGPU_FULL_MASK 0xffffffffu
+#define MCGPU_REGROUP_BLOCK 128
+
+__host__ __device__ inline int regroup_scratch_stride(int max_shells) { return max_shells | 1; }  // odd: conflict-free rows
 
 template <int BITS>
-__global__ void __launch_bounds__(128, 8) transport_regroup(const SceneDev sc, const __grid_constant__ mcgpu_view vw, long long stream_begin, long long stream_end,
-                                                            int histories_per_thread, int seed_input, int g1, int g2, unsigned long long* __restrict__ stream_counter,
-                                                            int w_threshold) {
+__global__ void __launch_bounds__(MCGPU_REGROUP_BLOCK, 8)
+    transport_regroup(const SceneDev sc, const __grid_constant__ mcgpu_view vw, long long stream_begin, long long stream_end, int histories_per_thread, int seed_input,
+                      int g1, int g2, unsigned long long* __restrict__ stream_counter, int w_threshold) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SharedTables& st = *reinterpret_cast<SharedTables*>(smem_raw);
   float4* sh_shells = reinterpret_cast<float4*>(smem_raw + ((sizeof(SharedTables) + 15) & ~size_t(15)));
-  float2* sh_palette = reinterpret_cast<float2*>(sh_shells + sc.num_slots * MCGPU_MAX_SHELLS);
+  float* sh_scratch = reinterpret_cast<float*>(sh_shells + sc.num_slots * MCGPU_MAX_SHELLS);
+  const int stride = regroup_scratch_stride(sc.max_shells);
+  float2* sh_palette = reinterpret_cast<float2*>(sh_scratch + (MCGPU_REGROUP_BLOCK / 32) * 32 * stride + ((MCGPU_REGROUP_BLOCK / 32) * 32 * stride & 1));
 
   for (int i = threadIdx.x; i < MCGPU_MAX_ENERGY_BINS; i += blockDim.x) {
     st.espc[i] = sc.spectrum->espc[i];
@@ -50,14 +62,15 @@ __global__ void __launch_bounds__(128, 8) transport_regroup(const SceneDev sc, c
   __syncthreads();
 
   const unsigned lane = threadIdx.x & 31u;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  float* wbuf = sh_scratch + (threadIdx.x >> 5) * 32 * stride;  // this warp's shell-term scratch [32][stride]
   const long long n_streams = stream_end - stream_begin;
 
   // per-lane photon / stream state (registers)
   Photon p;
   Ranecu rng;
-  RnLocal rn;
   mcgpu_mfp_record rec;
-  float mfp_woodcock = 0.f, mfp_density = 0.f;
+  float mfp_woodcock = 0.f, mfp_density = 0.f, s0 = 0.f;
   int index = 0, slot = 0, slot_old = -1, scatter_state = 0, hist_left = 0;
   int state = ST_I;
   p.x = p.y = p.z = p.u = p.v = p.w = p.E = 0.f;
@@ -121,7 +134,7 @@ __global__ void __launch_bounds__(128, 8) transport_regroup(const SceneDev sc, c
           if ((int)lane == leader) base = atomicAdd(stream_counter, (unsigned long long)__popc(m_i));
           base = __shfl_sync(MCGPU_FULL_MASK, base, leader);
           if (want) {
-            const long long s = (long long)base + __popc(m_i & ((1u << lane) - 1u));
+            const long long s = (long long)base + __popc(m_i & lt_mask);
             if (s < n_streams) {
               ranecu_init(rng, stream_begin + s, seed_input, g1, g2);
               hist_left = histories_per_thread;
@@ -143,19 +156,48 @@ __global__ void __launch_bounds__(128, 8) transport_regroup(const SceneDev sc, c
         slot_old = -1;
         state = enters ? ST_W : ST_T;  // a primary that misses the voxels can still hit the detector (K:240-241)
       }
-      // ---------------------------------------------------------------- C: Compton (K:290-326)
-      if (state == ST_C) {
-        const double costh = sample_compton(p.E, sh_shells + slot * MCGPU_MAX_SHELLS, sc.cmp_noscco[slot], rng, rn);
-        deflect(p, costh, 6.28318530717958647693 * rng.uniform_d());
-        index = __float2int_rd((p.E - sc.e0) * sc.ide);
-        if (index > -1) {
-          const float2 w = __ldg(&sc.woodcock[index]);
-          mfp_woodcock = w.x + p.E * w.y;
-          slot_old = -2;
-          scatter_state = (scatter_state == 0) ? 1 : 3;
-          state = ST_W;
-        } else {
-          state = ST_N;  // below the tabulated energies: absorbed (K:311, K:372)
+      // ---------------------------------------------------------------- C: Compton, S0 for fresh lanes (K:1315-1339)
+      {
+        const unsigned m_c = __ballot_sync(MCGPU_FULL_MASK, state == ST_C);
+        if (m_c) {
+          coop_shell_terms<0>(m_c, p.E, slot, 2.f, sh_shells, sc, wbuf, stride, lane);
+          if (state == ST_C) {
+            s0 = compton_ordered_sum(sh_shells + slot * MCGPU_MAX_SHELLS, sc.cmp_noscco[slot], wbuf + __popc(m_c & lt_mask) * stride);
+            state = ST_CT;
+          }
+          __syncwarp();
+        }
+      }
+      // ---------------------------------------------------------------- CT: one tau trial per lane (K:1342-1403), finish if accepted
+      {
+        const unsigned m_ct = __ballot_sync(MCGPU_FULL_MASK, state == ST_CT);
+        if (m_ct) {
+          const ComptonKin kin(p.E);
+          float tau = 1.f;
+          double cdt1 = 0.0;
+          if (state == ST_CT) cdt1 = compton_propose_tau(kin, p.E, rng, tau);
+          coop_shell_terms<1>(m_ct, p.E, slot, (float)cdt1, sh_shells, sc, wbuf, stride, lane);
+          if (state == ST_CT) {
+            const float4* shells = sh_shells + slot * MCGPU_MAX_SHELLS;
+            const int nosc = sc.cmp_noscco[slot];
+            const float* row = wbuf + __popc(m_ct & lt_mask) * stride;
+            const float s = compton_ordered_sum(shells, nosc, row);
+            if (compton_accept(kin, s0, s, tau, rng)) {
+              const double costh = compton_finish(p.E, s, tau, cdt1, shells, nosc, row, rng);
+              deflect(p, costh, 6.28318530717958647693 * rng.uniform_d());
+              index = __float2int_rd((p.E - sc.e0) * sc.ide);
+              if (index > -1) {
+                const float2 w = __ldg(&sc.woodcock[index]);
+                mfp_woodcock = w.x + p.E * w.y;
+                slot_old = -2;
+                scatter_state = (scatter_state == 0) ? 1 : 3;
+                state = ST_W;
+              } else {
+                state = ST_N;  // below the tabulated energies: absorbed (K:311, K:372)
+              }
+            }
+          }
+          __syncwarp();
         }
       }
       // ---------------------------------------------------------------- R: Rayleigh (K:329-347)
