@@ -235,7 +235,7 @@ extern "C" int mcgpu_dev_upload(struct mcgpu_device* d, const mcgpu_scene* s, co
     const char* k = getenv("MCGPU_KERNEL");
     const char* t = getenv("MCGPU_W_THRESHOLD");
     d->kernel_generation = (k && atoi(k) == 1) ? 1 : 2;
-    d->w_threshold = t ? atoi(t) : 12;
+    d->w_threshold = t ? atoi(t) : 8;
     if (d->w_threshold < 1) d->w_threshold = 1;
     if (d->w_threshold > 32) d->w_threshold = 32;
   }

@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(MCGPU_REGROUP_BLOCK, 8)
         if (m_c) {
           coop_shell_terms<0>(m_c, p.E, slot, 2.f, sh_shells, sc, wbuf, stride, lane);
           if (state == ST_C) {
-            s0 = compton_ordered_sum(sh_shells + slot * MCGPU_MAX_SHELLS, sc.cmp_noscco[slot], wbuf + __popc(m_c & lt_mask) * stride);
+            s0 = compton_ordered_sum<false>(sc.cmp_noscco[slot], wbuf + __popc(m_c & lt_mask) * stride);
             state = ST_CT;
           }
           __syncwarp();
@@ -180,8 +180,8 @@ __global__ void __launch_bounds__(MCGPU_REGROUP_BLOCK, 8)
           if (state == ST_CT) {
             const float4* shells = sh_shells + slot * MCGPU_MAX_SHELLS;
             const int nosc = sc.cmp_noscco[slot];
-            const float* row = wbuf + __popc(m_ct & lt_mask) * stride;
-            const float s = compton_ordered_sum(shells, nosc, row);
+            float* row = wbuf + __popc(m_ct & lt_mask) * stride;
+            const float s = compton_ordered_sum<true>(nosc, row);
             if (compton_accept(kin, s0, s, tau, rng)) {
               const double costh = compton_finish(p.E, s, tau, cdt1, shells, nosc, row, rng);
               deflect(p, costh, 6.28318530717958647693 * rng.uniform_d());

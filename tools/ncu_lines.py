@@ -63,3 +63,20 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def regions():
+    """function name per line of transport.cuh / regroup.cuh (top-level __device__ functions and kernel phases)"""
+    out = {}
+    for fname in ("transport.cuh", "regroup.cuh"):
+        text = (ROOT / "4d-cbct-mc_b200/csrc/cuda" / fname).read_text().splitlines()
+        cur = "-"
+        for i, l in enumerate(text, start=1):
+            m = re.match(r"\s*(?:template <[^>]*>\s*)?__device__ __forceinline__ [\w:<> &*]+?\s+(\w+)\(", l) or re.match(r"\s*__device__ __forceinline__ explicit (\w+)\(", l)
+            if m:
+                cur = m.group(1)
+            m = re.match(r"\s*// -{20,} (\w+):", l)
+            if m and fname == "regroup.cuh":
+                cur = "phase_" + m.group(1)
+            out[(fname, i)] = cur
+    return out
