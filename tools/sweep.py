@@ -34,10 +34,25 @@ def main():
         cfg = pkg.mcio.ScanConfig(n_histories=hist, n_projections=1 if wl == "air" else 894, source_position=pkg.mcio.default_source_position(ph.size_mm))
         inp = pkg.mcio.write_input(cfg, tmp / "x.vox", tmp, tmp / "input.in")
         base = None
-        configs = [(k, t) for k in kernels for t in (thresholds if k == 2 else [0])]
+        pools = [x for x in opts.get("pools", "2,3,4").split(",")]
+        tunes = [x for x in opts.get("tunes", "16:12:12:8").split(",")]  # th_w:th_n:th_c:th_r
+        configs = []
+        for k in kernels:
+            if k == 1:
+                configs.append((k, "0"))
+            elif k == 2:
+                configs += [(k, str(t)) for t in thresholds]
+            else:
+                configs += [(k, f"{pc}/{tu}") for pc in pools for tu in tunes]
         for k, t in configs:
             os.environ["MCGPU_KERNEL"] = str(k)
-            os.environ["MCGPU_W_THRESHOLD"] = str(t)
+            if k == 2:
+                os.environ["MCGPU_W_THRESHOLD"] = t
+            if k == 3:
+                pc, tu = t.split("/")
+                os.environ["MCGPU_POOL"] = pc
+                for name, val in zip(("W", "N", "C", "R"), tu.split(":")):
+                    os.environ[f"MCGPU_POOL_TH_{name}"] = val
             eng = pkg.engine.Engine([0])
             eng.load_input(inp).set_voxels(ph.materials, ph.densities, ph.spacing_cm).load_materials()
             info = eng.info
@@ -54,7 +69,7 @@ def main():
                 base = img
             rate = info.launched_histories / (min(ms) / 1e3)
             out[f"{wl}/k{k}/t{t}"] = {"hist_per_s": rate, "ms": min(ms), "identical_to_first": same}
-            print(f"{wl:10s} kernel v{k} thresh {t:2d}: {rate:.4g} hist/s ({min(ms):.1f} ms) identical={same}", flush=True)
+            print(f"{wl:10s} kernel v{k} cfg {t:>14s}: {rate:.4g} hist/s ({min(ms):.1f} ms) identical={same}", flush=True)
             eng.close()
     (ROOT / "gpurun_out").mkdir(exist_ok=True)
     (ROOT / "gpurun_out" / "sweep.json").write_text(json.dumps(out, indent=1))
