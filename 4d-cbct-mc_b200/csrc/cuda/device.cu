@@ -8,7 +8,6 @@
 
 #include <stdlib.h>
 
-#include "pool.cuh"
 #include "regroup.cuh"
 #include "transport.cuh"
 
@@ -43,10 +42,8 @@ struct mcgpu_device {
   unsigned long long* d_image;
   unsigned long long* d_peer_stage;  // used when peer access is unavailable
   unsigned long long* d_stream_counter;  // next stream of the running launch (regrouping kernel)
-  int kernel_generation;                 // 2 = regrouping warps (default), 3 = context pool (experimental), 1 = one thread per stream
+  int kernel_generation;                 // 2 = regrouping persistent warps (default), 1 = one thread per stream (reference structure, for A/B)
   int w_threshold;
-  int pool_contexts;                     // contexts per lane of generation 3
-  PoolTuning pool_tune;
   uint64_t* h_stage;
   int timed;
 };
@@ -237,22 +234,7 @@ extern "C" int mcgpu_dev_upload(struct mcgpu_device* d, const mcgpu_scene* s, co
   {  // tuning / A-B switches (documented in DESIGN.md); the defaults are the product path
     const char* k = getenv("MCGPU_KERNEL");
     const char* t = getenv("MCGPU_W_THRESHOLD");
-    d->kernel_generation = k ? atoi(k) : 2;
-    if (d->kernel_generation < 1 || d->kernel_generation > 3) d->kernel_generation = 2;
-    {
-      const char* pc = getenv("MCGPU_POOL");
-      const char* tw = getenv("MCGPU_POOL_TH_W");
-      const char* tn = getenv("MCGPU_POOL_TH_N");
-      const char* tc = getenv("MCGPU_POOL_TH_C");
-      const char* tr = getenv("MCGPU_POOL_TH_R");
-      d->pool_contexts = pc ? atoi(pc) : 3;
-      if (d->pool_contexts < 2) d->pool_contexts = 2;
-      if (d->pool_contexts > 4) d->pool_contexts = 4;
-      d->pool_tune.th_w = tw ? atoi(tw) : 16;
-      d->pool_tune.th_n = tn ? atoi(tn) : 12;
-      d->pool_tune.th_c = tc ? atoi(tc) : 12;
-      d->pool_tune.th_r = tr ? atoi(tr) : 8;
-    }
+    d->kernel_generation = (k && atoi(k) == 1) ? 1 : 2;
     d->w_threshold = t ? atoi(t) : 8;
     if (d->w_threshold < 1) d->w_threshold = 1;
     if (d->w_threshold > 32) d->w_threshold = 32;
@@ -313,33 +295,11 @@ extern "C" int mcgpu_dev_launch(struct mcgpu_device* d, const mcgpu_view* view, 
     const int g1 = pow_mod_host(40014, leap, 2147483563LL), g2 = pow_mod_host(40692, leap, 2147483399LL);
     size_t smem = ((sizeof(SharedTables) + 15) & ~size_t(15)) + sizeof(float4) * d->scene.num_slots * MCGPU_MAX_SHELLS;
     if (d->voxel_bits == 4 || d->voxel_bits == 8) smem += sizeof(float2) * d->scene.palette_size;
-#define LAUNCH_POOL_P(B, PP)                                                                                                             \
-  {                                                                                                                                      \
-    int per_sm = 0;                                                                                                                      \
-    const size_t psmem = pool_smem_bytes(d->scene.num_slots, d->scene.max_shells, d->scene.palette_size, PP, (B) == 4 || (B) == 8);      \
-    CK(cudaFuncSetAttribute(transport_pool<B, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));                            \
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, transport_pool<B, PP>, MCGPU_POOL_BLOCK, psmem));                          \
-    long long pgrid = (long long)d->sm_count * (per_sm > 0 ? per_sm : 1);                                                                \
-    const long long need = (n_streams + (long long)MCGPU_POOL_BLOCK * PP - 1) / ((long long)MCGPU_POOL_BLOCK * PP);                      \
-    if (pgrid > need) pgrid = need;                                                                                                      \
-    CK(cudaMemsetAsync(d->d_stream_counter, 0, sizeof(unsigned long long), d->stream));                                                  \
-    transport_pool<B, PP><<<(unsigned)pgrid, MCGPU_POOL_BLOCK, psmem, d->stream>>>(d->scene, *view, l->stream_begin, l->stream_end,      \
-                                                                                   l->histories_per_thread, l->seed_input, g1, g2,       \
-                                                                                   d->d_stream_counter, d->pool_tune);                   \
-  }
-#define LAUNCH_POOL(B)                                                                                                                   \
-  switch (d->pool_contexts) {                                                                                                            \
-    case 2: LAUNCH_POOL_P(B, 2) break;                                                                                                   \
-    case 4: LAUNCH_POOL_P(B, 4) break;                                                                                                   \
-    default: LAUNCH_POOL_P(B, 3) break;                                                                                                  \
-  }
 #define LAUNCH(B)                                                                                                                        \
   if (d->kernel_generation == 1) {                                                                                                       \
     CK(cudaFuncSetAttribute(transport_streams<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                              \
     transport_streams<B><<<(unsigned)grid, block, smem, d->stream>>>(d->scene, *view, l->stream_begin, l->stream_end, l->histories_per_thread, \
                                                                      l->seed_input, g1, g2);                                            \
-  } else if (d->kernel_generation == 3) {                                                                                                \
-    LAUNCH_POOL(B)                                                                                                                       \
   } else {                                                                                                                               \
     int per_sm = 0;                                                                                                                      \
     smem += sizeof(float) * (MCGPU_REGROUP_BLOCK / 32) * 32 * regroup_scratch_stride(d->scene.max_shells);                               \
@@ -358,8 +318,6 @@ extern "C" int mcgpu_dev_launch(struct mcgpu_device* d, const mcgpu_view* view, 
       default: LAUNCH(64) break;
     }
 #undef LAUNCH
-#undef LAUNCH_POOL
-#undef LAUNCH_POOL_P
     CK(cudaGetLastError());
   }
   CK(cudaEventRecord(d->ev1, d->stream));

@@ -156,11 +156,13 @@ __global__ void __launch_bounds__(MCGPU_REGROUP_BLOCK, 8)
         slot_old = -1;
         state = enters ? ST_W : ST_T;  // a primary that misses the voxels can still hit the detector (K:240-241)
       }
-      // ---------------------------------------------------------------- C: Compton, S0 for fresh lanes (K:1315-1339)
+      // ---------------------------------------------------------------- C: Compton, S0 for fresh events (K:1315-1339)
+      double costh = 0.0;
+      bool deflect_pending = false;
       {
         const unsigned m_c = __ballot_sync(MCGPU_FULL_MASK, state == ST_C);
         if (m_c) {
-          coop_shell_terms<0>(m_c, p.E, slot, 2.f, sh_shells, sc, wbuf, stride, lane);
+          coop_shell_terms(m_c, p.E, slot, 2.f, false, sh_shells, sc, wbuf, stride, lane);
           if (state == ST_C) {
             s0 = compton_ordered_sum<false>(sc.cmp_noscco[slot], wbuf + __popc(m_c & lt_mask) * stride);
             state = ST_CT;
@@ -168,7 +170,7 @@ __global__ void __launch_bounds__(MCGPU_REGROUP_BLOCK, 8)
           __syncwarp();
         }
       }
-      // ---------------------------------------------------------------- CT: one tau trial per lane (K:1342-1403), finish if accepted
+      // ---------------------------------------------------------------- CT: one tau trial per lane (K:1342-1403), rest of GCOa if accepted
       {
         const unsigned m_ct = __ballot_sync(MCGPU_FULL_MASK, state == ST_CT);
         if (m_ct) {
@@ -176,25 +178,14 @@ __global__ void __launch_bounds__(MCGPU_REGROUP_BLOCK, 8)
           float tau = 1.f;
           double cdt1 = 0.0;
           if (state == ST_CT) cdt1 = compton_propose_tau(kin, p.E, rng, tau);
-          coop_shell_terms<1>(m_ct, p.E, slot, (float)cdt1, sh_shells, sc, wbuf, stride, lane);
+          coop_shell_terms(m_ct, p.E, slot, (float)cdt1, true, sh_shells, sc, wbuf, stride, lane);
           if (state == ST_CT) {
-            const float4* shells = sh_shells + slot * MCGPU_MAX_SHELLS;
             const int nosc = sc.cmp_noscco[slot];
             float* row = wbuf + __popc(m_ct & lt_mask) * stride;
             const float s = compton_ordered_sum<true>(nosc, row);
             if (compton_accept(kin, s0, s, tau, rng)) {
-              const double costh = compton_finish(p.E, s, tau, cdt1, shells, nosc, row, rng);
-              deflect(p, costh, 6.28318530717958647693 * rng.uniform_d());
-              index = __float2int_rd((p.E - sc.e0) * sc.ide);
-              if (index > -1) {
-                const float2 w = __ldg(&sc.woodcock[index]);
-                mfp_woodcock = w.x + p.E * w.y;
-                slot_old = -2;
-                scatter_state = (scatter_state == 0) ? 1 : 3;
-                state = ST_W;
-              } else {
-                state = ST_N;  // below the tabulated energies: absorbed (K:311, K:372)
-              }
+              costh = compton_finish(p.E, s, tau, cdt1, sh_shells + slot * MCGPU_MAX_SHELLS, nosc, row, rng);
+              deflect_pending = true;
             }
           }
           __syncwarp();
@@ -202,10 +193,27 @@ __global__ void __launch_bounds__(MCGPU_REGROUP_BLOCK, 8)
       }
       // ---------------------------------------------------------------- R: Rayleigh (K:329-347)
       if (state == ST_R) {
-        const double costh = sample_rayleigh(sc, p.E, slot, rec.pmax_next, rng);
+        costh = sample_rayleigh(sc, p.E, slot, rec.pmax_next, rng);
+        deflect_pending = true;
+      }
+      // ---------------------------------------------------------------- new direction for both kinds of scattering (K:299, K:339)
+      if (deflect_pending) {
         deflect(p, costh, 6.28318530717958647693 * rng.uniform_d());
-        scatter_state = (scatter_state == 0) ? 2 : 3;
-        state = ST_W;
+        if (state == ST_R) {
+          scatter_state = (scatter_state == 0) ? 2 : 3;
+          state = ST_W;
+        } else {
+          index = __float2int_rd((p.E - sc.e0) * sc.ide);
+          if (index > -1) {
+            const float2 w = __ldg(&sc.woodcock[index]);
+            mfp_woodcock = w.x + p.E * w.y;
+            slot_old = -2;
+            scatter_state = (scatter_state == 0) ? 1 : 3;
+            state = ST_W;
+          } else {
+            state = ST_N;  // below the tabulated energies: absorbed (K:311, K:372)
+          }
+        }
       }
     }
   }

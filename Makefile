@@ -31,7 +31,7 @@ $(BUILD)/%.o: $(HOSTDIR)/%.c $(HOSTDIR)/mcgpu_host.h include/mcgpu_b200.h
 	@mkdir -p $(BUILD)
 	$(CC) $(CFLAGS) -c $< -o $@
 
-$(BUILD)/device.o: $(CUDADIR)/device.cu $(CUDADIR)/transport.cuh $(CUDADIR)/regroup.cuh $(CUDADIR)/pool.cuh $(HOSTDIR)/mcgpu_host.h
+$(BUILD)/device.o: $(CUDADIR)/device.cu $(CUDADIR)/transport.cuh $(CUDADIR)/regroup.cuh $(HOSTDIR)/mcgpu_host.h
 	@mkdir -p $(BUILD)
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(BUILD)/ptxas_device.log || (cat $(BUILD)/ptxas_device.log; false)
 	@grep -E "registers|spill" $(BUILD)/ptxas_device.log | sort | uniq -c | head -20
