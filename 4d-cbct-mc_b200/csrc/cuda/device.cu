@@ -295,21 +295,26 @@ extern "C" int mcgpu_dev_launch(struct mcgpu_device* d, const mcgpu_view* view, 
     const int g1 = pow_mod_host(40014, leap, 2147483563LL), g2 = pow_mod_host(40692, leap, 2147483399LL);
     size_t smem = ((sizeof(SharedTables) + 15) & ~size_t(15)) + sizeof(float4) * d->scene.num_slots * MCGPU_MAX_SHELLS;
     if (d->voxel_bits == 4 || d->voxel_bits == 8) smem += sizeof(float2) * d->scene.palette_size;
+#define LAUNCH_REGROUP(B)                                                                                                                \
+  {                                                                                                                                      \
+    int per_sm = 0;                                                                                                                      \
+    CK(cudaFuncSetAttribute(transport_regroup<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                          \
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, transport_regroup<B>, block, smem));                                   \
+    long long pgrid = (long long)d->sm_count * (per_sm > 0 ? per_sm : 1);                                                                \
+    if (pgrid > grid) pgrid = grid;                                                                                                      \
+    CK(cudaMemsetAsync(d->d_stream_counter, 0, sizeof(unsigned long long), d->stream));                                                  \
+    transport_regroup<B><<<(unsigned)pgrid, block, smem, d->stream>>>(d->scene, *view, l->stream_begin, l->stream_end,               \
+                                                                          l->histories_per_thread, l->seed_input, g1, g2,                \
+                                                                          d->d_stream_counter, d->w_threshold);                          \
+  }
 #define LAUNCH(B)                                                                                                                        \
   if (d->kernel_generation == 1) {                                                                                                       \
     CK(cudaFuncSetAttribute(transport_streams<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                              \
     transport_streams<B><<<(unsigned)grid, block, smem, d->stream>>>(d->scene, *view, l->stream_begin, l->stream_end, l->histories_per_thread, \
                                                                      l->seed_input, g1, g2);                                            \
   } else {                                                                                                                               \
-    int per_sm = 0;                                                                                                                      \
-    smem += sizeof(float) * (MCGPU_REGROUP_BLOCK / 32) * 32 * regroup_scratch_stride(d->scene.max_shells);                               \
-    CK(cudaFuncSetAttribute(transport_regroup<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                              \
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, transport_regroup<B>, block, smem));                                       \
-    long long pgrid = (long long)d->sm_count * (per_sm > 0 ? per_sm : 1);                                                                \
-    if (pgrid > grid) pgrid = grid;                                                                                                      \
-    CK(cudaMemsetAsync(d->d_stream_counter, 0, sizeof(unsigned long long), d->stream));                                                  \
-    transport_regroup<B><<<(unsigned)pgrid, block, smem, d->stream>>>(d->scene, *view, l->stream_begin, l->stream_end, l->histories_per_thread, \
-                                                                      l->seed_input, g1, g2, d->d_stream_counter, d->w_threshold);      \
+    smem += sizeof(float) * (MCGPU_REGROUP_BLOCK / 32) * MCGPU_SCRATCH_ROWS * regroup_scratch_stride(d->scene.max_shells) + 8;           \
+    LAUNCH_REGROUP(B)                                                                                                                    \
   }
     switch (d->voxel_bits) {
       case 4: LAUNCH(4) break;
@@ -318,6 +323,7 @@ extern "C" int mcgpu_dev_launch(struct mcgpu_device* d, const mcgpu_view* view, 
       default: LAUNCH(64) break;
     }
 #undef LAUNCH
+#undef LAUNCH_REGROUP
     CK(cudaGetLastError());
   }
   CK(cudaEventRecord(d->ev1, d->stream));

@@ -38,6 +38,13 @@ enum LaneState : int { ST_W = 0, ST_C = 1, ST_CT = 2, ST_R = 3, ST_T = 4, ST_N =
 #define MCGPU_REGROUP_BLOCK 128
 
 __host__ __device__ inline int regroup_scratch_stride(int max_shells) { return max_shells | 1; }  // odd: conflict-free rows
+#define MCGPU_SCRATCH_ROWS 16  // photons per cooperative Compton call; further lanes wait for the next event phase
+
+// keep the lowest MCGPU_SCRATCH_ROWS set bits of a lane mask
+__device__ __forceinline__ unsigned limit_rows(unsigned m) {
+  while (__popc(m) > MCGPU_SCRATCH_ROWS) m &= ~(0x80000000u >> __clz(m));
+  return m;
+}
 
 template <int BITS>
 __global__ void __launch_bounds__(MCGPU_REGROUP_BLOCK, 8)
@@ -48,7 +55,7 @@ __global__ void __launch_bounds__(MCGPU_REGROUP_BLOCK, 8)
   float4* sh_shells = reinterpret_cast<float4*>(smem_raw + ((sizeof(SharedTables) + 15) & ~size_t(15)));
   float* sh_scratch = reinterpret_cast<float*>(sh_shells + sc.num_slots * MCGPU_MAX_SHELLS);
   const int stride = regroup_scratch_stride(sc.max_shells);
-  float2* sh_palette = reinterpret_cast<float2*>(sh_scratch + (MCGPU_REGROUP_BLOCK / 32) * 32 * stride + ((MCGPU_REGROUP_BLOCK / 32) * 32 * stride & 1));
+  float2* sh_palette = reinterpret_cast<float2*>(sh_scratch + (MCGPU_REGROUP_BLOCK / 32) * MCGPU_SCRATCH_ROWS * stride + ((MCGPU_REGROUP_BLOCK / 32) * MCGPU_SCRATCH_ROWS * stride & 1));
 
   for (int i = threadIdx.x; i < MCGPU_MAX_ENERGY_BINS; i += blockDim.x) {
     st.espc[i] = sc.spectrum->espc[i];
@@ -63,7 +70,7 @@ __global__ void __launch_bounds__(MCGPU_REGROUP_BLOCK, 8)
 
   const unsigned lane = threadIdx.x & 31u;
   const unsigned lt_mask = (1u << lane) - 1u;
-  float* wbuf = sh_scratch + (threadIdx.x >> 5) * 32 * stride;  // this warp's shell-term scratch [32][stride]
+  float* wbuf = sh_scratch + (threadIdx.x >> 5) * MCGPU_SCRATCH_ROWS * stride;  // this warp's shell-term scratch [rows][stride]
   const long long n_streams = stream_end - stream_begin;
 
   // per-lane photon / stream state (registers)
@@ -160,10 +167,10 @@ __global__ void __launch_bounds__(MCGPU_REGROUP_BLOCK, 8)
       double costh = 0.0;
       bool deflect_pending = false;
       {
-        const unsigned m_c = __ballot_sync(MCGPU_FULL_MASK, state == ST_C);
+        const unsigned m_c = limit_rows(__ballot_sync(MCGPU_FULL_MASK, state == ST_C));
         if (m_c) {
           coop_shell_terms(m_c, p.E, slot, 2.f, false, sh_shells, sc, wbuf, stride, lane);
-          if (state == ST_C) {
+          if ((m_c >> lane) & 1u) {
             s0 = compton_ordered_sum<false>(sc.cmp_noscco[slot], wbuf + __popc(m_c & lt_mask) * stride);
             state = ST_CT;
           }
@@ -172,14 +179,15 @@ __global__ void __launch_bounds__(MCGPU_REGROUP_BLOCK, 8)
       }
       // ---------------------------------------------------------------- CT: one tau trial per lane (K:1342-1403), rest of GCOa if accepted
       {
-        const unsigned m_ct = __ballot_sync(MCGPU_FULL_MASK, state == ST_CT);
+        const unsigned m_ct = limit_rows(__ballot_sync(MCGPU_FULL_MASK, state == ST_CT));
         if (m_ct) {
+          const bool mine = (m_ct >> lane) & 1u;
           const ComptonKin kin(p.E);
           float tau = 1.f;
           double cdt1 = 0.0;
-          if (state == ST_CT) cdt1 = compton_propose_tau(kin, p.E, rng, tau);
+          if (mine) cdt1 = compton_propose_tau(kin, p.E, rng, tau);
           coop_shell_terms(m_ct, p.E, slot, (float)cdt1, true, sh_shells, sc, wbuf, stride, lane);
-          if (state == ST_CT) {
+          if (mine) {
             const int nosc = sc.cmp_noscco[slot];
             float* row = wbuf + __popc(m_ct & lt_mask) * stride;
             const float s = compton_ordered_sum<true>(nosc, row);

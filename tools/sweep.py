@@ -22,7 +22,7 @@ def main():
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
     opts = dict(a[2:].split("=") for a in sys.argv[1:] if a.startswith("--") and "=" in a)
     hist = int(opts.get("hist", 100_000_000))
-    thresholds = [int(x) for x in opts.get("thresholds", "4,8,12,16,20,24").split(",")]
+    thresholds = opts.get("thresholds", "8:8").split(",")  # w_threshold:min_blocks
     kernels = [int(x) for x in opts.get("kernels", "1,2").split(",")]
     workloads = args or ["thorax", "catphan"]
     factories = {"thorax": pkg.phantoms.thorax, "catphan": pkg.phantoms.catphan604, "water": pkg.phantoms.water_cylinder,
@@ -41,7 +41,7 @@ def main():
             if k == 1:
                 configs.append((k, "0"))
             elif k == 2:
-                configs += [(k, str(t)) for t in thresholds]
+                configs += [(k, t) for t in thresholds]
             else:
                 configs += [(k, f"{pc}/{tu}") for pc in pools for tu in tunes]
         for k, t in configs:
