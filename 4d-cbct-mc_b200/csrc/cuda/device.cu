@@ -41,6 +41,9 @@ struct mcgpu_device {
   mcgpu_spectrum* d_spectrum;
   unsigned long long* d_image;
   unsigned long long* d_peer_stage;  // used when peer access is unavailable
+  unsigned long long* d_materials_dose;  // [25][2] or NULL
+  unsigned long long* d_voxels_edep;     // [roi][2] or NULL
+  long long dose_roi_voxels;
   unsigned long long* d_stream_counter;  // next stream of the running launch (regrouping kernel)
   int kernel_generation;                 // 2 = regrouping persistent warps (default), 1 = one thread per stream (reference structure, for A/B)
   int w_threshold;
@@ -119,7 +122,9 @@ __global__ void __launch_bounds__(128) transport_streams(const SceneDev sc, cons
 
         prob += mfp_density * (rec.ay + p.E * rec.by);
         if (randno < prob) {  // Compton (K:290-326)
+          const float e_before = p.E;
           const double costh = sample_compton(p.E, sh_shells + slot * MCGPU_MAX_SHELLS, sc.cmp_noscco[slot], rng, rn);
+          deposit_energy(sc, p, slot, -1.0f * (p.E - e_before));
           deflect(p, costh, 6.28318530717958647693 * rng.uniform_d());
           index = __float2int_rd((p.E - sc.e0) * sc.ide);
           if (index > -1) {
@@ -135,6 +140,7 @@ __global__ void __launch_bounds__(128) transport_streams(const SceneDev sc, cons
             deflect(p, costh, 6.28318530717958647693 * rng.uniform_d());
             scatter_state = (scatter_state == 0) ? 2 : 3;
           } else {
+            deposit_energy(sc, p, slot, p.E);
             index = -11;  // photoelectric absorption (K:348-353)
           }
         }
@@ -187,6 +193,8 @@ static void free_scene_allocs(mcgpu_device* d) {
   cudaFree(d->d_volume), cudaFree(d->d_palette), cudaFree(d->d_mfp), cudaFree(d->d_woodcock);
   cudaFree(d->d_ray_xpab), cudaFree(d->d_ray_itl_itu), cudaFree(d->d_cmp_shells), cudaFree(d->d_spectrum);
   cudaFree(d->d_image), cudaFree(d->d_peer_stage), cudaFree(d->d_stream_counter);
+  cudaFree(d->d_materials_dose), cudaFree(d->d_voxels_edep);
+  d->d_materials_dose = NULL, d->d_voxels_edep = NULL;
   d->d_stream_counter = NULL;
   if (d->h_stage) cudaFreeHost(d->h_stage);
   d->d_volume = NULL, d->d_palette = NULL, d->d_mfp = NULL, d->d_woodcock = NULL, d->d_ray_xpab = NULL;
@@ -231,6 +239,16 @@ extern "C" int mcgpu_dev_upload(struct mcgpu_device* d, const mcgpu_scene* s, co
   if (upload(&d->d_image, NULL, sizeof(unsigned long long) * d->image_words, err, errlen)) return -1;
   CK(cudaMemset(d->d_image, 0, sizeof(unsigned long long) * d->image_words));
   CK(cudaMalloc((void**)&d->d_stream_counter, sizeof(unsigned long long)));
+  d->dose_roi_voxels = 0;
+  if (s->tally_material_dose) {
+    CK(cudaMalloc((void**)&d->d_materials_dose, sizeof(unsigned long long) * 2 * MCGPU_MAX_MATERIALS));
+    CK(cudaMemset(d->d_materials_dose, 0, sizeof(unsigned long long) * 2 * MCGPU_MAX_MATERIALS));
+  }
+  if (s->tally_voxel_dose) {
+    d->dose_roi_voxels = s->dose_roi_voxels;
+    CK(cudaMalloc((void**)&d->d_voxels_edep, sizeof(unsigned long long) * 2 * (size_t)s->dose_roi_voxels));
+    CK(cudaMemset(d->d_voxels_edep, 0, sizeof(unsigned long long) * 2 * (size_t)s->dose_roi_voxels));
+  }
   {  // tuning / A-B switches (documented in DESIGN.md); the defaults are the product path
     const char* k = getenv("MCGPU_KERNEL");
     const char* t = getenv("MCGPU_W_THRESHOLD");
@@ -265,6 +283,10 @@ extern "C" int mcgpu_dev_upload(struct mcgpu_device* d, const mcgpu_scene* s, co
   }
   sc.e0 = s->e0;
   sc.ide = s->ide;
+  sc.materials_dose = d->d_materials_dose;
+  sc.voxels_edep = d->d_voxels_edep;
+  for (int k = 0; k < 6; k++) sc.dose_roi[k] = s->dose_roi[k];
+  for (int k = 0; k < MCGPU_MAX_MATERIALS; k++) sc.material_of_slot[k] = s->material_of_slot[k];
   d->voxel_bits = s->voxel_bits;
   return 0;
 }
@@ -367,5 +389,37 @@ extern "C" int mcgpu_dev_accumulate_peer(struct mcgpu_device* dst, struct mcgpu_
   accumulate_u64<<<dst->sm_count * 4, 256, 0, dst->stream>>>(dst->d_image, from, n);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(dst->stream));
+  return 0;
+}
+
+extern "C" int mcgpu_dev_reset_dose(struct mcgpu_device* d, char* err, size_t errlen) {
+  CK(cudaSetDevice(d->ordinal));
+  if (d->d_materials_dose) CK(cudaMemsetAsync(d->d_materials_dose, 0, sizeof(unsigned long long) * 2 * MCGPU_MAX_MATERIALS, d->stream));
+  if (d->d_voxels_edep) CK(cudaMemsetAsync(d->d_voxels_edep, 0, sizeof(unsigned long long) * 2 * (size_t)d->dose_roi_voxels, d->stream));
+  CK(cudaStreamSynchronize(d->stream));
+  return 0;
+}
+
+extern "C" int mcgpu_dev_add_dose(struct mcgpu_device* d, uint64_t* materials, uint64_t* voxels, char* err, size_t errlen) {
+  CK(cudaSetDevice(d->ordinal));
+  CK(cudaStreamSynchronize(d->stream));
+  if (materials && d->d_materials_dose) {
+    unsigned long long tmp[2 * MCGPU_MAX_MATERIALS];
+    CK(cudaMemcpy(tmp, d->d_materials_dose, sizeof tmp, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 2 * MCGPU_MAX_MATERIALS; k++) materials[k] += tmp[k];
+  }
+  if (voxels && d->d_voxels_edep) {
+    const size_t n = 2 * (size_t)d->dose_roi_voxels;
+    unsigned long long* tmp = (unsigned long long*)malloc(sizeof(unsigned long long) * n);
+    if (!tmp) {
+      snprintf(err, errlen, "out of memory fetching the voxel dose");
+      return -1;
+    }
+    cudaError_t e = cudaMemcpy(tmp, d->d_voxels_edep, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess)
+      for (size_t k = 0; k < n; k++) voxels[k] += tmp[k];
+    free(tmp);
+    CK(e);
+  }
   return 0;
 }

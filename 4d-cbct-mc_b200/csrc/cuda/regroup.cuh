@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(MCGPU_REGROUP_BLOCK, 8)
   const unsigned lt_mask = (1u << lane) - 1u;
   float* wbuf = sh_scratch + (threadIdx.x >> 5) * MCGPU_SCRATCH_ROWS * stride;  // this warp's shell-term scratch [rows][stride]
   const long long n_streams = stream_end - stream_begin;
+  const bool dose_on = sc.materials_dose != nullptr || sc.voxels_edep != nullptr;
 
   // per-lane photon / stream state (registers)
   Photon p;
@@ -121,6 +122,7 @@ __global__ void __launch_bounds__(MCGPU_REGROUP_BLOCK, 8)
             } else {
               prob += mfp_density * (rec.az + p.E * rec.bz);
               state = (randno < prob) ? ST_R : ST_N;  // else: photoelectric absorption, history over
+              if (dose_on && state == ST_N) deposit_energy(sc, p, slot, p.E);  // K:351: all of E is deposited
             }
           }
         }
@@ -192,7 +194,9 @@ __global__ void __launch_bounds__(MCGPU_REGROUP_BLOCK, 8)
             float* row = wbuf + __popc(m_ct & lt_mask) * stride;
             const float s = compton_ordered_sum<true>(nosc, row);
             if (compton_accept(kin, s0, s, tau, rng)) {
+              const float e_before = p.E;
               costh = compton_finish(p.E, s, tau, cdt1, sh_shells + slot * MCGPU_MAX_SHELLS, nosc, row, rng);
+              if (dose_on) deposit_energy(sc, p, slot, -1.0f * (p.E - e_before));  // K:296-301, 359
               deflect_pending = true;
             }
           }

@@ -229,54 +229,78 @@ typedef struct scan_worker {
   char err[512];
 } scan_worker;
 
+static void scan_publish(scan_shared* sh, int p, int status, double dt) {
+  pthread_mutex_lock(&sh->mu);
+  sh->done[p] = status;
+  sh->seconds[p] = dt;
+  pthread_cond_broadcast(&sh->cv);
+  pthread_mutex_unlock(&sh->mu);
+}
+
+/* One host thread per device.  The projection loop is software-pipelined: while the GPU transports
+ * projection p the thread formats and writes the ASCII file of its previous projection (64 MB of
+ * text, ~0.1 s), so reporting costs no GPU time (the reference serialises kernel and fprintf, H:861-1040). */
 static void* scan_thread(void* arg) {
   scan_worker* w = (scan_worker*)arg;
   scan_shared* sh = w->sh;
   mcgpu_ctx* ctx = sh->ctx;
   const int P = ctx->in.num_projections, n = ctx->num_devices;
   const size_t words = (size_t)4 * ctx->views[0].total_num_pixels;
-  uint64_t* image = (uint64_t*)malloc(words * sizeof(uint64_t));
-  int p;
-  for (p = w->device; p < P; p += n) {
-    int status = 1;
-    double t0 = now_s(), dt = 0.0;
-    if (!image) {
+  uint64_t* image[2];
+  int p, cur = 0, prev = -1, failed = 0;
+  double prev_dt = 0.0;
+  image[0] = (uint64_t*)malloc(words * sizeof(uint64_t));
+  image[1] = (uint64_t*)malloc(words * sizeof(uint64_t));
+  for (p = w->device; p < P && !failed; p += n) {
+    double t0 = now_s();
+    float ms;
+    int launched = 0;
+    if (!image[0] || !image[1]) {
       snprintf(w->err, sizeof w->err, "out of memory for the host image");
-      status = MCGPU_E_NOMEM;
-    } else if (projection_skipped(ctx, p)) {
-      status = 2;
+      scan_publish(sh, p, MCGPU_E_NOMEM, 0.0);
+      break;
+    }
+    if (projection_skipped(ctx, p)) {
+      scan_publish(sh, p, 2, 0.0);
     } else {
       mcgpu_launch l;
-      float ms;
       l.histories_per_thread = sh->hpt;
       l.seed_input = sh->seeds[p];
       l.threads_per_block = ctx->in.threads_per_block;
       l.stream_begin = 0;
       l.stream_end = (long long)sh->blocks * ctx->in.threads_per_block;
       l.zero_image = 1;
-      if (mcgpu_dev_launch(ctx->dev[w->device], &ctx->views[p], &l, w->err, sizeof w->err) != 0 || mcgpu_dev_sync(ctx->dev[w->device], &ms, w->err, sizeof w->err) != 0 ||
-          mcgpu_dev_fetch(ctx->dev[w->device], image, w->err, sizeof w->err) != 0)
-        status = MCGPU_E_CUDA;
-      dt = now_s() - t0;
-      if (status == 1) {
-        /* report_image only reads ctx; each worker writes its own file */
-        int verbose = ctx->verbose, rc;
-        (void)verbose;
-        rc = mcgpu_write_projection_ascii(ctx, p, image, dt);
-        if (rc != MCGPU_OK) {
-          snprintf(w->err, sizeof w->err, "%s", ctx->err);
-          status = rc;
-        }
+      if (mcgpu_dev_launch(ctx->dev[w->device], &ctx->views[p], &l, w->err, sizeof w->err) != 0) {
+        scan_publish(sh, p, MCGPU_E_CUDA, 0.0);
+        failed = 1;
+      } else
+        launched = 1;
+    }
+    if (prev >= 0) { /* overlapped with the kernel just launched */
+      const int rc = mcgpu_write_projection_ascii(ctx, prev, image[cur ^ 1], prev_dt);
+      if (rc != MCGPU_OK) snprintf(w->err, sizeof w->err, "%s", ctx->err);
+      scan_publish(sh, prev, rc == MCGPU_OK ? 1 : rc, prev_dt);
+      if (rc != MCGPU_OK) failed = 1;
+      prev = -1;
+    }
+    if (launched) {
+      if (mcgpu_dev_sync(ctx->dev[w->device], &ms, w->err, sizeof w->err) != 0 || mcgpu_dev_fetch(ctx->dev[w->device], image[cur], w->err, sizeof w->err) != 0) {
+        scan_publish(sh, p, MCGPU_E_CUDA, 0.0);
+        failed = 1;
+      } else {
+        prev = p;
+        prev_dt = now_s() - t0;
+        cur ^= 1;
       }
     }
-    pthread_mutex_lock(&sh->mu);
-    sh->done[p] = status;
-    sh->seconds[p] = dt;
-    pthread_cond_broadcast(&sh->cv);
-    pthread_mutex_unlock(&sh->mu);
-    if (status < 0) break;
   }
-  free(image);
+  if (prev >= 0) {
+    const int rc = mcgpu_write_projection_ascii(ctx, prev, image[cur ^ 1], prev_dt);
+    if (rc != MCGPU_OK) snprintf(w->err, sizeof w->err, "%s", ctx->err);
+    scan_publish(sh, prev, rc == MCGPU_OK ? 1 : rc, prev_dt);
+  }
+  free(image[0]);
+  free(image[1]);
   return NULL;
 }
 
@@ -285,6 +309,7 @@ int mcgpu_run_all(mcgpu_ctx* ctx, mcgpu_progress_cb cb, void* user) {
   if ((rc = ready_to_run(ctx, 0)) != MCGPU_OK) return rc;
   P = ctx->in.num_projections;
   n = ctx->num_devices;
+  if ((rc = mcgpu_reset_dose(ctx)) != MCGPU_OK) return rc;
 
   if (P < n) { /* fewer projections than devices: split each projection's histories instead */
     const size_t words = (size_t)4 * ctx->views[0].total_num_pixels;
@@ -300,6 +325,7 @@ int mcgpu_run_all(mcgpu_ctx* ctx, mcgpu_progress_cb cb, void* user) {
       if (cb) cb(p, P, dt, user);
     }
     free(image);
+    if (rc == MCGPU_OK) rc = mcgpu_write_dose_reports(ctx, 0.0, P);
     return rc;
   }
 
@@ -372,6 +398,7 @@ int mcgpu_run_all(mcgpu_ctx* ctx, mcgpu_progress_cb cb, void* user) {
     pthread_mutex_destroy(&sh.mu);
     pthread_cond_destroy(&sh.cv);
     free(workers), free(threads), free(sh.done), free(sh.seconds), free(sh.seeds);
+    if (rc == MCGPU_OK) rc = mcgpu_write_dose_reports(ctx, 0.0, P);
     return rc;
   }
 }
@@ -457,4 +484,53 @@ long long mcgpu_copy_table(const mcgpu_ctx* ctx, const char* name, void* out, si
   if (bytes > cap) bytes = cap;
   memcpy(out, src, bytes);
   return (long long)bytes;
+}
+
+/* ---- dose tallies (optional; K:357-369, reports H:2976-3263) ------------------------------ */
+
+int mcgpu_reset_dose(mcgpu_ctx* ctx) {
+  int d;
+  if (!ctx || !ctx->have_tables) return MCGPU_E_STATE;
+  for (d = 0; d < ctx->num_devices; d++)
+    if (mcgpu_dev_reset_dose(ctx->dev[d], ctx->err, sizeof ctx->err) != 0) return MCGPU_E_CUDA;
+  return MCGPU_OK;
+}
+
+long long mcgpu_get_dose(mcgpu_ctx* ctx, const char* which, uint64_t* out, size_t cap_words) {
+  const int materials = which && !strcmp(which, "materials");
+  size_t words;
+  int d;
+  if (!ctx || !ctx->have_tables || !which || (!materials && strcmp(which, "voxels"))) return MCGPU_E_ARG;
+  if (materials ? !ctx->scene.tally_material_dose : !ctx->scene.tally_voxel_dose) return 0;
+  words = materials ? (size_t)2 * MCGPU_MAX_MATERIALS : (size_t)2 * (size_t)ctx->scene.dose_roi_voxels;
+  if (!out) return (long long)words;
+  if (cap_words < words) return mcgpu_fail(ctx, MCGPU_E_ARG, "get_dose: buffer of %zu words, %zu needed", cap_words, words);
+  memset(out, 0, words * sizeof(uint64_t));
+  for (d = 0; d < ctx->num_devices; d++)
+    if (mcgpu_dev_add_dose(ctx->dev[d], materials ? out : NULL, materials ? NULL : out, ctx->err, sizeof ctx->err) != 0) return MCGPU_E_CUDA;
+  return (long long)words;
+}
+
+int mcgpu_write_dose_reports(mcgpu_ctx* ctx, double seconds, int projections_simulated) {
+  int rc = MCGPU_OK;
+  if (!ctx || !ctx->have_tables) return MCGPU_E_STATE;
+  if (projections_simulated < 1) projections_simulated = ctx->in.num_projections;
+  if (ctx->scene.tally_voxel_dose) {
+    const long long words = mcgpu_get_dose(ctx, "voxels", NULL, 0);
+    uint64_t* buf = (uint64_t*)malloc((size_t)words * sizeof(uint64_t));
+    if (!buf) return mcgpu_fail(ctx, MCGPU_E_NOMEM, "dose report: out of memory");
+    if (mcgpu_get_dose(ctx, "voxels", buf, (size_t)words) < 0)
+      rc = MCGPU_E_CUDA;
+    else
+      rc = mcgpu_write_dose_files(ctx, buf, seconds, projections_simulated);
+    free(buf);
+  }
+  if (rc == MCGPU_OK && ctx->scene.tally_material_dose) {
+    uint64_t md[2 * MCGPU_MAX_MATERIALS];
+    if (mcgpu_get_dose(ctx, "materials", md, 2 * MCGPU_MAX_MATERIALS) < 0)
+      rc = MCGPU_E_CUDA;
+    else
+      rc = mcgpu_print_materials_dose(ctx, md, projections_simulated);
+  }
+  return rc;
 }

@@ -121,6 +121,10 @@ typedef struct mcgpu_scene {
   /* palette remapped to slots */
   int palette_size, voxel_bits;
   mcgpu_f2* palette;      /* [palette_size] = (density, slot as int bits) */
+  /* optional dose tallies (SECTION DOSE DEPOSITION, H:1619-1709), ROI clipped to the volume (H:2057-2065) */
+  int tally_material_dose, tally_voxel_dose;
+  int dose_roi[6];        /* x_min,x_max,y_min,y_max,z_min,z_max, 0-based inclusive */
+  long long dose_roi_voxels;
 } mcgpu_scene;
 
 struct mcgpu_device; /* opaque, csrc/cuda/device.cu */
@@ -178,6 +182,11 @@ int mcgpu_dev_fetch(struct mcgpu_device* d, uint64_t* host, char* err, size_t er
 /* dst += src over NVLink peer access (or staged copy when peer access is unavailable) */
 int mcgpu_dev_accumulate_peer(struct mcgpu_device* dst, struct mcgpu_device* src, char* err, size_t errlen);
 void* mcgpu_dev_image_ptr(struct mcgpu_device* d);
+/* dose tallies accumulate over launches until reset; fetch ADDS the device's counters to the host arrays */
+int mcgpu_dev_reset_dose(struct mcgpu_device* d, char* err, size_t errlen);
+int mcgpu_dev_add_dose(struct mcgpu_device* d, uint64_t* materials_2x25, uint64_t* voxels_2xroi, char* err, size_t errlen);
+int mcgpu_write_dose_files(mcgpu_ctx* ctx, const uint64_t* voxels_edep, double seconds, int projections); /* dose.c */
+int mcgpu_print_materials_dose(mcgpu_ctx* ctx, const uint64_t* materials_dose, int projections);         /* dose.c */
 
 #ifdef __cplusplus
 }

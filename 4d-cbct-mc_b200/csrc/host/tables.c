@@ -334,6 +334,20 @@ int mcgpu_build_scene(mcgpu_ctx* ctx) {
       d[2] = t->cmp_fj0[m + i * MCGPU_MAX_MATERIALS];
     }
   }
+  s->tally_material_dose = ctx->have_input && ctx->in.flag_material_dose == 1;
+  s->tally_voxel_dose = 0;
+  s->dose_roi_voxels = 0;
+  if (ctx->have_input && ctx->in.flag_voxel_dose == 1) { /* clip the ROI to the volume like load_voxels (H:2057-2065) */
+    const int nv[3] = {v->nx, v->ny, v->nz};
+    for (i = 0; i < 3; i++) {
+      s->dose_roi[2 * i] = ctx->in.dose_roi[2 * i];
+      s->dose_roi[2 * i + 1] = ctx->in.dose_roi[2 * i + 1] < nv[i] - 1 ? ctx->in.dose_roi[2 * i + 1] : nv[i] - 1;
+    }
+    if (s->dose_roi[0] <= s->dose_roi[1] && s->dose_roi[2] <= s->dose_roi[3] && s->dose_roi[4] <= s->dose_roi[5]) {
+      s->tally_voxel_dose = 1;
+      s->dose_roi_voxels = (long long)(s->dose_roi[1] - s->dose_roi[0] + 1) * (s->dose_roi[3] - s->dose_roi[2] + 1) * (s->dose_roi[5] - s->dose_roi[4] + 1);
+    }
+  }
   s->voxel_bits = v->voxel_bits;
   s->palette_size = v->palette_size;
   if (v->palette_size > 0) {

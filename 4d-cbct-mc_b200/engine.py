@@ -52,6 +52,9 @@ _SIGS = {
     "mcgpu_run_all": (C.c_int, [C.c_void_p, PROGRESS_CB, C.c_void_p]),
     "mcgpu_write_projection_ascii": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_double]),
     "mcgpu_projection_filename": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_size_t]),
+    "mcgpu_reset_dose": (C.c_int, [C.c_void_p]),
+    "mcgpu_get_dose": (C.c_longlong, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t]),
+    "mcgpu_write_dose_reports": (C.c_int, [C.c_void_p, C.c_double, C.c_int]),
     "mcgpu_get_info": (C.c_int, [C.c_void_p, C.POINTER(Info)]),
     "mcgpu_projection_seed": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
     "mcgpu_copy_table": (C.c_longlong, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t]),
@@ -204,6 +207,20 @@ class Engine:
     def run_all(self, progress: Callable[[int, int, float], None] | None = None):
         cb = PROGRESS_CB((lambda p, n, s, u: progress(p, n, s)) if progress else (lambda p, n, s, u: None))
         self._check(_lib.mcgpu_run_all(self._h, cb, None))
+
+    def reset_dose(self):
+        self._check(_lib.mcgpu_reset_dose(self._h))
+
+    def dose(self, which: str) -> np.ndarray:
+        """uint64 [n, 2] dose counters ("materials": n = 25, "voxels": n = ROI voxels); empty when off."""
+        n = self._check(_lib.mcgpu_get_dose(self._h, which.encode(), None, 0))
+        out = np.zeros(n, dtype=np.uint64)
+        if n:
+            self._check(_lib.mcgpu_get_dose(self._h, which.encode(), out.ctypes.data, n))
+        return out.reshape(-1, 2)
+
+    def write_dose_reports(self, seconds: float = 0.0, projections: int = 0):
+        self._check(_lib.mcgpu_write_dose_reports(self._h, seconds, projections))
 
     def write_projection(self, p: int, image: np.ndarray, seconds: float = 0.0):
         img = np.ascontiguousarray(image, dtype=np.uint64)

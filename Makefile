@@ -16,7 +16,7 @@ CFLAGS   := -std=gnu11 -O2 -g -fPIC -Wall -Wextra -Wno-unused-result -ffp-contra
 NVFLAGS  := -std=c++17 -O3 -lineinfo -fmad=false -gencode arch=compute_100a,code=sm_100a \
             -Xcompiler -fPIC -Iinclude -I$(HOSTDIR) -Xptxas -v
 
-HOST_SRC := input.c geometry.c voxels.c tables.c ranecu_host.c report.c api.c
+HOST_SRC := input.c geometry.c voxels.c tables.c ranecu_host.c report.c dose.c api.c
 HOST_OBJ := $(HOST_SRC:%.c=$(BUILD)/%.o)
 CUDA_OBJ := $(BUILD)/device.o
 

@@ -125,6 +125,19 @@ int mcgpu_write_projection_ascii(mcgpu_ctx* ctx, int p, const uint64_t* image, d
 /* Name report_image gives the file of projection p; returns strlen or <0. */
 int mcgpu_projection_filename(const mcgpu_ctx* ctx, int p, char* out, size_t out_len);
 
+/* ---- dose tallies (optional) ------------------------------------------------------------ */
+
+/* tally_materials_dose / tally_voxel_energy_deposition (K:1547-1563, K:418-443), enabled by the .in's
+ * SECTION DOSE DEPOSITION (off in every cbctmc run).  The counters accumulate over run calls, like the
+ * reference accumulates them over projections; mcgpu_run_all resets them first and writes the reports
+ * at the end.  which = "materials": uint64[25][2] (sum of round(Edep*100), sum of round(Edep^2)) by
+ * material number; "voxels": uint64[ROI voxels][2], x fastest inside the ROI.  out==NULL returns the
+ * number of words (0 when the tally is off). */
+int mcgpu_reset_dose(mcgpu_ctx* ctx);
+long long mcgpu_get_dose(mcgpu_ctx* ctx, const char* which, uint64_t* out, size_t cap_words);
+/* report_voxels_dose + report_materials_dose (H:2976-3263): '<dose file>', '.raw', '_2sigma.raw'. */
+int mcgpu_write_dose_reports(mcgpu_ctx* ctx, double seconds, int projections_simulated);
+
 /* ---- introspection (tests, bindings) ---------------------------------------------------- */
 
 int mcgpu_get_info(const mcgpu_ctx* ctx, mcgpu_info* out);

@@ -193,3 +193,56 @@ def test_history_split_across_two_gpus_is_bit_identical(pkg, cases):
     assert np.array_equal(one.run_projection(3), two.run_projection(3))
     one.close()
     two.close()
+
+
+def test_dose_tallies_match_reference_cuda_source(pkg, oracle_py, tmp_path):
+    """SECTION DOSE DEPOSITION enabled (never the case in cbctmc): voxel-dose files byte-identical to the
+    reference's, material dose consistent with the voxel dose."""
+    if not oracle_py.REF_CUDA_EXACT.exists():
+        pytest.skip("oracle/_ref/MC-GPU_v1.3_sm100_exact.x was not built")
+    ph = pkg.phantoms.thorax(shape=(64, 64, 25), spacing_mm=8.0)
+    roi = ((5, 60), (3, 64), (2, 20))
+    outs = {}
+    for who in ("ref", "ours"):
+        d = tmp_path / who
+        d.mkdir()
+        vox = pkg.mcio.write_vox(d / "geometry.vox.gz", ph.materials, ph.densities, ph.spacing_cm)
+        cfg = pkg.mcio.ScanConfig(n_histories=150_000, n_detector_pixels=(66, 28), n_projections=3, angle_between_projections=120.0,
+                                  source_position=pkg.mcio.default_source_position(ph.size_mm), tally_material_dose=True, tally_voxel_dose=True, dose_roi=roi)
+        outs[who] = (d, pkg.mcio.write_input(cfg, vox, d, d / "input.in"))
+    log = oracle_py.run_reference_binary(oracle_py.REF_CUDA_EXACT, outs["ref"][1], cwd=outs["ref"][0])
+    assert "VOXEL ROI DOSE TALLY REPORT" in log and "MATERIALS TOTAL DOSE TALLY REPORT" in log
+    eng = pkg.engine.Engine([0])
+    eng.load_input(outs["ours"][1]).load_voxels().load_materials()
+    eng.run_all()
+    for name in ("dose.dat.raw", "dose.dat_2sigma.raw"):
+        a, b = (outs["ref"][0] / name).read_bytes(), (outs["ours"][0] / name).read_bytes()
+        assert len(a) == 56 * 62 * 19 * 4 and a == b, name
+    strip = lambda p: [l for l in p.read_text().splitlines() if not l.startswith("#")]  # noqa: E731
+    assert strip(outs["ref"][0] / "dose.dat") == strip(outs["ours"][0] / "dose.dat")
+    vox = eng.dose("voxels")
+    mat = eng.dose("materials")
+    assert vox.shape == (56 * 62 * 19, 2) and mat.shape == (25, 2)
+    assert vox[:, 0].sum() > 0 and mat[:, 0].sum() >= vox[:, 0].sum()  # the ROI is a subset of the volume
+    # projections are unchanged by the extra tallies
+    for p in range(3):
+        f = Path(eng.projection_filename(p))
+        ref = outs["ref"][0] / f.name
+        assert [l for l in f.read_text().splitlines() if not l.startswith("#")] == [l for l in ref.read_text().splitlines() if not l.startswith("#")]
+    # accumulate-until-reset semantics and the full-volume identity: material dose == sum of voxel dose
+    eng.close()
+    d = tmp_path / "full"
+    d.mkdir()
+    cfg = pkg.mcio.ScanConfig(n_histories=150_000, n_detector_pixels=(66, 28), source_position=pkg.mcio.default_source_position(ph.size_mm),
+                              tally_material_dose=True, tally_voxel_dose=True, dose_roi=((1, 64), (1, 64), (1, 25)))
+    inp = pkg.mcio.write_input(cfg, tmp_path / "ours" / "geometry.vox.gz", d, d / "input.in")
+    eng = pkg.engine.Engine([0])
+    eng.load_input(inp).load_voxels().load_materials()
+    eng.run_projection(0)
+    once = eng.dose("materials").copy()
+    assert once[:, 0].sum() == eng.dose("voxels")[:, 0].sum() and once[:, 1].sum() == eng.dose("voxels")[:, 1].sum()
+    eng.run_projection(0)
+    assert np.array_equal(eng.dose("materials"), 2 * once)
+    eng.reset_dose()
+    assert eng.dose("materials").sum() == 0
+    eng.close()
