@@ -1,0 +1,53 @@
+// Internals shared by device.cu (device management) and launch.cu (kernels + launch, built twice:
+// exact arithmetic and fast-math).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "transport.cuh"
+#include "regroup.cuh"
+
+#define CK(call)                                                                                    \
+  do {                                                                                              \
+    cudaError_t e_ = (call);                                                                        \
+    if (e_ != cudaSuccess) {                                                                        \
+      snprintf(err, errlen, "CUDA failure %s at %s:%d (%s)", cudaGetErrorName(e_), __FILE__, __LINE__, #call); \
+      return -1;                                                                                    \
+    }                                                                                               \
+  } while (0)
+
+struct mcgpu_device {
+  int ordinal;
+  int sm_count;
+  cudaStream_t stream;
+  cudaEvent_t ev0, ev1;
+  McgpuSceneDev scene;
+  int voxel_bits;
+  size_t image_words;
+  // owned allocations
+  void* d_volume;
+  float2* d_palette;
+  mcgpu_mfp_record* d_mfp;
+  float2* d_woodcock;
+  float4* d_ray_xpab;
+  uchar2* d_ray_itl_itu;
+  float4* d_cmp_shells;
+  mcgpu_spectrum* d_spectrum;
+  unsigned long long* d_image;
+  unsigned long long* d_peer_stage;  // used when peer access is unavailable
+  unsigned long long* d_materials_dose;  // [25][2] or NULL
+  unsigned long long* d_voxels_edep;     // [roi][2] or NULL
+  long long dose_roi_voxels;
+  unsigned long long* d_stream_counter;  // next stream of the running launch (regrouping kernel)
+  int kernel_generation;                 // 2 = regrouping persistent warps (default), 1 = one thread per stream (reference structure, for A/B)
+  int w_threshold;
+  int fast_math;                         // 0 = bit-exact arithmetic (default), 1 = the reference's shipped -use_fast_math flags
+  uint64_t* h_stage;
+  int timed;
+};
+
+
+extern "C" int mcgpu_launch_exact(struct mcgpu_device* d, const mcgpu_view* view, const mcgpu_launch* l, char* err, size_t errlen);
+extern "C" int mcgpu_launch_fast(struct mcgpu_device* d, const mcgpu_view* view, const mcgpu_launch* l, char* err, size_t errlen);

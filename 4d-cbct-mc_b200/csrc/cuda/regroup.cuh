@@ -30,7 +30,10 @@
 #pragma once
 #include "transport.cuh"
 
-namespace mcgpu {
+#ifndef MCGPU_NS
+#define MCGPU_NS mcgpu
+#endif
+namespace MCGPU_NS {
 
 enum LaneState : int { ST_W = 0, ST_C = 1, ST_CT = 2, ST_R = 3, ST_T = 4, ST_N = 5, ST_I = 6, ST_F = 7 };
 
@@ -46,7 +49,7 @@ __device__ __forceinline__ unsigned limit_rows(unsigned m) {
   return m;
 }
 
-template <int BITS>
+template <int BITS, bool DOSE>
 __global__ void __launch_bounds__(MCGPU_REGROUP_BLOCK, 8)
     transport_regroup(const SceneDev sc, const __grid_constant__ mcgpu_view vw, long long stream_begin, long long stream_end, int histories_per_thread, int seed_input,
                       int g1, int g2, unsigned long long* __restrict__ stream_counter, int w_threshold) {
@@ -72,7 +75,6 @@ __global__ void __launch_bounds__(MCGPU_REGROUP_BLOCK, 8)
   const unsigned lt_mask = (1u << lane) - 1u;
   float* wbuf = sh_scratch + (threadIdx.x >> 5) * MCGPU_SCRATCH_ROWS * stride;  // this warp's shell-term scratch [rows][stride]
   const long long n_streams = stream_end - stream_begin;
-  const bool dose_on = sc.materials_dose != nullptr || sc.voxels_edep != nullptr;
 
   // per-lane photon / stream state (registers)
   Photon p;
@@ -122,7 +124,7 @@ __global__ void __launch_bounds__(MCGPU_REGROUP_BLOCK, 8)
             } else {
               prob += mfp_density * (rec.az + p.E * rec.bz);
               state = (randno < prob) ? ST_R : ST_N;  // else: photoelectric absorption, history over
-              if (dose_on && state == ST_N) deposit_energy(sc, p, slot, p.E);  // K:351: all of E is deposited
+              if (DOSE && state == ST_N) deposit_energy(sc, p, slot, p.E);  // K:351: all of E is deposited
             }
           }
         }
@@ -196,7 +198,7 @@ __global__ void __launch_bounds__(MCGPU_REGROUP_BLOCK, 8)
             if (compton_accept(kin, s0, s, tau, rng)) {
               const float e_before = p.E;
               costh = compton_finish(p.E, s, tau, cdt1, sh_shells + slot * MCGPU_MAX_SHELLS, nosc, row, rng);
-              if (dose_on) deposit_energy(sc, p, slot, -1.0f * (p.E - e_before));  // K:296-301, 359
+              if (DOSE) deposit_energy(sc, p, slot, -1.0f * (p.E - e_before));  // K:296-301, 359
               deflect_pending = true;
             }
           }
@@ -231,4 +233,4 @@ __global__ void __launch_bounds__(MCGPU_REGROUP_BLOCK, 8)
   }
 }
 
-}  // namespace mcgpu
+}  // namespace MCGPU_NS

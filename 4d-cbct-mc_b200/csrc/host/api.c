@@ -113,6 +113,14 @@ int mcgpu_set_histories(mcgpu_ctx* ctx, unsigned long long total_histories) {
   return MCGPU_OK;
 }
 
+int mcgpu_set_fast_math(mcgpu_ctx* ctx, int on) {
+  int d;
+  if (!ctx) return MCGPU_E_ARG;
+  ctx->fast_math = on != 0;
+  for (d = 0; d < ctx->num_devices; d++) mcgpu_dev_set_fast_math(ctx->dev[d], ctx->fast_math);
+  return MCGPU_OK;
+}
+
 int mcgpu_set_seed(mcgpu_ctx* ctx, int seed) {
   if (!ctx || !ctx->have_input) return MCGPU_E_STATE;
   ctx->in.seed_input = seed;
@@ -409,6 +417,7 @@ int mcgpu_get_info(const mcgpu_ctx* ctx, mcgpu_info* out) {
   if (!ctx || !out) return MCGPU_E_ARG;
   memset(out, 0, sizeof *out);
   out->num_devices = ctx->num_devices;
+  out->fast_math = ctx->fast_math;
   if (ctx->have_input) {
     const mcgpu_view* v = &ctx->views[0];
     hpt = ctx->hpt_current ? ctx->hpt_current : ctx->in.histories_per_thread;

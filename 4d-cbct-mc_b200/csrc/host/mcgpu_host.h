@@ -144,6 +144,7 @@ struct mcgpu_ctx {
   int num_devices;
   struct mcgpu_device** dev;
   double last_kernel_ms;
+  int fast_math;
 };
 
 /* ---- host stages (each returns MCGPU_OK or an error code, message in ctx->err) ---------- */
@@ -182,6 +183,7 @@ int mcgpu_dev_fetch(struct mcgpu_device* d, uint64_t* host, char* err, size_t er
 /* dst += src over NVLink peer access (or staged copy when peer access is unavailable) */
 int mcgpu_dev_accumulate_peer(struct mcgpu_device* dst, struct mcgpu_device* src, char* err, size_t errlen);
 void* mcgpu_dev_image_ptr(struct mcgpu_device* d);
+void mcgpu_dev_set_fast_math(struct mcgpu_device* d, int on);
 /* dose tallies accumulate over launches until reset; fetch ADDS the device's counters to the host arrays */
 int mcgpu_dev_reset_dose(struct mcgpu_device* d, char* err, size_t errlen);
 int mcgpu_dev_add_dose(struct mcgpu_device* d, uint64_t* materials_2x25, uint64_t* voxels_2xroi, char* err, size_t errlen);

@@ -29,7 +29,7 @@ class Info(C.Structure):
         "num_materials_used", "num_energy_values", "num_spectrum_bins", "threads_per_block", "histories_per_thread",
         "num_blocks", "seed_input", "enable_specific_angles", "num_devices", "voxel_bits", "palette_size")] + [
         ("requested_histories", C.c_ulonglong), ("launched_histories", C.c_ulonglong),
-        ("mean_energy_spectrum", C.c_float), ("e0", C.c_float), ("ide", C.c_float)]
+        ("mean_energy_spectrum", C.c_float), ("e0", C.c_float), ("ide", C.c_float), ("fast_math", C.c_int)]
 
 
 PROGRESS_CB = C.CFUNCTYPE(None, C.c_int, C.c_int, C.c_double, C.c_void_p)
@@ -45,6 +45,7 @@ _SIGS = {
     "mcgpu_load_materials": (C.c_int, [C.c_void_p, C.POINTER(C.c_char_p), C.c_int]),
     "mcgpu_set_histories": (C.c_int, [C.c_void_p, C.c_ulonglong]),
     "mcgpu_set_seed": (C.c_int, [C.c_void_p, C.c_int]),
+    "mcgpu_set_fast_math": (C.c_int, [C.c_void_p, C.c_int]),
     "mcgpu_run_projection": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "mcgpu_run_streams": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.c_longlong, C.c_void_p]),
     "mcgpu_device_image": (C.c_void_p, [C.c_void_p]),
@@ -154,6 +155,10 @@ class Engine:
 
     def set_seed(self, seed: int):
         self._check(_lib.mcgpu_set_seed(self._h, seed))
+
+    def set_fast_math(self, on: bool):
+        """False (default): bit-exact arithmetic.  True: the reference's shipped -use_fast_math flags."""
+        self._check(_lib.mcgpu_set_fast_math(self._h, int(on)))
 
     # -- info
     @property

@@ -13,12 +13,13 @@ NVCC     ?= nvcc
 # -ffp-contract=off: the table builders must round exactly like the reference's host code
 CFLAGS   := -std=gnu11 -O2 -g -fPIC -Wall -Wextra -Wno-unused-result -ffp-contract=off -Iinclude -I$(HOSTDIR)
 # -fmad=false and no fast-math: bit-exact tallies against the reference CUDA source
-NVFLAGS  := -std=c++17 -O3 -lineinfo -fmad=false -gencode arch=compute_100a,code=sm_100a \
-            -Xcompiler -fPIC -Iinclude -I$(HOSTDIR) -Xptxas -v
+NVFLAGS  := -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a \
+            -Xcompiler -fPIC -Iinclude -I$(HOSTDIR)
 
 HOST_SRC := input.c geometry.c voxels.c tables.c ranecu_host.c report.c dose.c api.c
 HOST_OBJ := $(HOST_SRC:%.c=$(BUILD)/%.o)
-CUDA_OBJ := $(BUILD)/device.o
+CUDA_OBJ := $(BUILD)/device.o $(BUILD)/launch_exact.o $(BUILD)/launch_fast.o
+CUDA_HDR := $(CUDADIR)/transport.cuh $(CUDADIR)/regroup.cuh $(CUDADIR)/scene_dev.h $(CUDADIR)/device_internal.h $(HOSTDIR)/mcgpu_host.h
 
 all: lib exe oracle
 
@@ -31,10 +32,20 @@ $(BUILD)/%.o: $(HOSTDIR)/%.c $(HOSTDIR)/mcgpu_host.h include/mcgpu_b200.h
 	@mkdir -p $(BUILD)
 	$(CC) $(CFLAGS) -c $< -o $@
 
-$(BUILD)/device.o: $(CUDADIR)/device.cu $(CUDADIR)/transport.cuh $(CUDADIR)/regroup.cuh $(HOSTDIR)/mcgpu_host.h
+$(BUILD)/device.o: $(CUDADIR)/device.cu $(CUDA_HDR)
 	@mkdir -p $(BUILD)
-	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(BUILD)/ptxas_device.log || (cat $(BUILD)/ptxas_device.log; false)
-	@grep -E "registers|spill" $(BUILD)/ptxas_device.log | sort | uniq -c | head -20
+	$(NVCC) $(NVFLAGS) -fmad=false -c $< -o $@
+
+# the kernels, twice: bit-exact arithmetic (default path) and the reference's shipped fast-math flags (opt-in)
+$(BUILD)/launch_exact.o: $(CUDADIR)/launch.cu $(CUDA_HDR)
+	@mkdir -p $(BUILD)
+	$(NVCC) $(NVFLAGS) -fmad=false -Xptxas -v -c $< -o $@ 2> $(BUILD)/ptxas_exact.log || (cat $(BUILD)/ptxas_exact.log; false)
+	@grep -E "registers|spill" $(BUILD)/ptxas_exact.log | sort | uniq -c | head -20
+
+$(BUILD)/launch_fast.o: $(CUDADIR)/launch.cu $(CUDA_HDR)
+	@mkdir -p $(BUILD)
+	$(NVCC) $(NVFLAGS) -use_fast_math -DMCGPU_FAST_MATH -DMCGPU_NS=mcgpu_fast -Xptxas -v -c $< -o $@ 2> $(BUILD)/ptxas_fast.log || (cat $(BUILD)/ptxas_fast.log; false)
+	@grep -E "registers|spill" $(BUILD)/ptxas_fast.log | sort | uniq -c | head -20
 
 $(LIBDIR)/libmcgpu_b200.so: $(HOST_OBJ) $(CUDA_OBJ)
 	@mkdir -p $(LIBDIR)

@@ -62,6 +62,7 @@ typedef struct mcgpu_info {
   unsigned long long launched_histories;  /* blocks*tpb*hpt (H:841) */
   float mean_energy_spectrum;   /* eV (H:3575) */
   float e0, ide;                /* MFP energy grid (H:2308, H:2337) */
+  int fast_math;                /* 0 = bit-exact arithmetic (default), 1 = reference's shipped fast-math flags */
 } mcgpu_info;
 
 typedef void (*mcgpu_progress_cb)(int projection_index, int num_projections, double seconds, void* user);
@@ -94,6 +95,10 @@ int mcgpu_load_materials(mcgpu_ctx* ctx, const char* const* paths, int n_paths);
 /* Overrides of the .in values, applied before the next run (used by benchmarks / bindings). */
 int mcgpu_set_histories(mcgpu_ctx* ctx, unsigned long long total_histories);
 int mcgpu_set_seed(mcgpu_ctx* ctx, int seed);
+/* Arithmetic of the transport kernels.  0 (default): -fmad=false, no fast-math -- tallies bit-identical to
+ * the reference CUDA source compiled the same way.  1: the flags the reference ships with
+ * (docker/compile.sh:36, -use_fast_math) -- faster, statistically equivalent results only. */
+int mcgpu_set_fast_math(mcgpu_ctx* ctx, int on);
 
 /* ---- simulation ------------------------------------------------------------------------- */
 

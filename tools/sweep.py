@@ -55,6 +55,7 @@ def main():
                     os.environ[f"MCGPU_POOL_TH_{name}"] = val
             eng = pkg.engine.Engine([0])
             eng.load_input(inp).set_voxels(ph.materials, ph.densities, ph.spacing_cm).load_materials()
+            eng.set_fast_math("fast" in opts)
             info = eng.info
             n = info.num_blocks * info.threads_per_block
             p = 0 if wl == "air" else 100
