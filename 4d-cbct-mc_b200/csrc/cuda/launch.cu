@@ -138,15 +138,15 @@ extern "C" int MCGPU_LAUNCH_NAME(struct mcgpu_device* d, const mcgpu_view* view,
     const int g1 = pow_mod_host(40014, leap, 2147483563LL), g2 = pow_mod_host(40692, leap, 2147483399LL);
     size_t smem = ((sizeof(SharedTables) + 15) & ~size_t(15)) + sizeof(float4) * d->scene.num_slots * MCGPU_MAX_SHELLS;
     if (d->voxel_bits == 4 || d->voxel_bits == 8) smem += sizeof(float2) * d->scene.palette_size;
-#define LAUNCH_REGROUP_D(B, DOSE_)                                                                                                           \
+#define LAUNCH_REGROUP_D(B, DOSE_, ROT_)                                                                                                           \
   {                                                                                                                                      \
     int per_sm = 0;                                                                                                                      \
-    CK(cudaFuncSetAttribute(transport_regroup<B, DOSE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                          \
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, transport_regroup<B, DOSE_>, block, smem));                                   \
+    CK(cudaFuncSetAttribute(transport_regroup<B, DOSE_, ROT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                          \
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, transport_regroup<B, DOSE_, ROT_>, block, smem));                                   \
     long long pgrid = (long long)d->sm_count * (per_sm > 0 ? per_sm : 1);                                                                \
     if (pgrid > grid) pgrid = grid;                                                                                                      \
     CK(cudaMemsetAsync(d->d_stream_counter, 0, sizeof(unsigned long long), d->stream));                                                  \
-    transport_regroup<B, DOSE_><<<(unsigned)pgrid, block, smem, d->stream>>>(d->scene, *view, l->stream_begin, l->stream_end,               \
+    transport_regroup<B, DOSE_, ROT_><<<(unsigned)pgrid, block, smem, d->stream>>>(d->scene, *view, l->stream_begin, l->stream_end,               \
                                                                           l->histories_per_thread, l->seed_input, g1, g2,                \
                                                                           d->d_stream_counter, d->w_threshold);                          \
   }
@@ -158,9 +158,9 @@ extern "C" int MCGPU_LAUNCH_NAME(struct mcgpu_device* d, const mcgpu_view* view,
   } else {                                                                                                                               \
     smem += sizeof(float) * (MCGPU_REGROUP_BLOCK / 32) * MCGPU_SCRATCH_ROWS * regroup_scratch_stride(d->scene.max_shells) + 8;           \
     if (d->scene.materials_dose || d->scene.voxels_edep) {                                                                               \
-      LAUNCH_REGROUP_D(B, true)                                                                                                          \
+      LAUNCH_REGROUP_D(B, true, -1)                                                                                                        \
     } else {                                                                                                                             \
-      LAUNCH_REGROUP_D(B, false)                                                                                                         \
+      if (view->rotation_flag == 1) { LAUNCH_REGROUP_D(B, false, 1) } else { LAUNCH_REGROUP_D(B, false, 0) }                                                                                                        \
     }                                                                                                                                    \
   }
     switch (d->voxel_bits) {

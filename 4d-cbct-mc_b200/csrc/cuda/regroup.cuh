@@ -49,7 +49,7 @@ __device__ __forceinline__ unsigned limit_rows(unsigned m) {
   return m;
 }
 
-template <int BITS, bool DOSE>
+template <int BITS, bool DOSE, int ROT>
 __global__ void __launch_bounds__(MCGPU_REGROUP_BLOCK, 8)
     transport_regroup(const SceneDev sc, const __grid_constant__ mcgpu_view vw, long long stream_begin, long long stream_end, int histories_per_thread, int seed_input,
                       int g1, int g2, unsigned long long* __restrict__ stream_counter, int w_threshold) {
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(MCGPU_REGROUP_BLOCK, 8)
     } else {
       // ---------------------------------------------------------------- T: detector tally (K:377-381)
       if (state == ST_T) {
-        tally_photon(sc, vw, p, scatter_state);
+        tally_photon<ROT>(sc, vw, p, scatter_state);
         state = ST_N;
       }
       // ---------------------------------------------------------------- I: next stream of the launch (K:198)
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(MCGPU_REGROUP_BLOCK, 8)
       // ---------------------------------------------------------------- N: next history (K:210-234)
       if (state == ST_N) {
         hist_left--;
-        const bool enters = emit_photon(sc, vw, st, rng, p);
+        const bool enters = emit_photon<ROT>(sc, vw, st, rng, p);
         scatter_state = 0;
         index = __float2int_rd((p.E - sc.e0) * sc.ide);
         const float2 w = __ldg(&sc.woodcock[index]);

@@ -149,3 +149,48 @@ def test_spectrum_outside_table_range_is_rejected(pkg, cases, tmp_path):
         with pytest.raises(pkg.engine.McgpuError) as e:
             eng.load_materials()
         assert e.value.code == -1 and "outside the tabulated energy interval" in str(e.value)
+
+
+def test_fast_density_scanner_equals_strtof(pkg, cases, tmp_path):
+    """The streaming ingest scans densities with integer arithmetic; every value must equal glibc's
+    strtof (what the reference's sscanf("%f") gives), including exponent forms and long mantissas."""
+    import ctypes
+
+    libc = ctypes.CDLL("libc.so.6")
+    libc.strtof.restype = ctypes.c_float
+    libc.strtof.argtypes = [ctypes.c_char_p, ctypes.c_void_p]
+    rng = np.random.default_rng(11)
+    n = 60000
+    vals = np.concatenate([rng.random(n // 2) * 3.0, 10.0 ** rng.uniform(-8.5, 1.5, n // 2)])
+    fmts = ["%.6f", "%.3f", "%.9f", "%.12f", "%.17g", "%.7e", "%g", "%.1f0000"]
+    tokens = []
+    for i, v in enumerate(vals):
+        tok = fmts[i % len(fmts)] % v
+        if float(tok) < 1e-9:
+            tok = "0.001300"
+        tokens.append(tok)
+    tokens[:6] = ["1", "2.", ".5", "1e0", "+0.25", "0.0013000000000000000001"]
+    body = "".join(f"{1 + i % 22} {t}\n" for i, t in enumerate(tokens))
+    vox = tmp_path / "dens.vox"
+    vox.write_text(f"[SECTION VOXELS HEADER v.2008-04-13]\n{n} 1 1\n1.0 1.0 1.0\n[END OF VXH SECTION]\n" + body)
+    inp, _, _ = cases["water_p1"]
+    with pkg.engine.Engine() as eng:
+        eng.load_input(inp).load_voxels(vox)
+        got = eng.table("voxel_density")
+    want = np.array([libc.strtof(t.encode(), None) for t in tokens], dtype=np.float32)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_large_file_spans_many_blocks_and_ignores_trailing_lines(pkg, cases, tmp_path):
+    """More than one 4 MB block, rows separated by the blank lines cbctmc writes, extra lines after the last voxel."""
+    ph = pkg.phantoms.thorax(shape=(96, 96, 60), spacing_mm=4.0)
+    vox = pkg.mcio.write_vox(tmp_path / "big.vox", ph.materials, ph.densities, ph.spacing_cm)
+    assert vox.stat().st_size > 5 * (4 << 20) // 4
+    with open(vox, "a") as f:
+        f.write("\n# trailing comment\n7 1.000000\n")
+    inp, _, _ = cases["water_p1"]
+    with pkg.engine.Engine() as eng:
+        eng.load_input(inp).load_voxels(vox)
+        assert np.array_equal(eng.table("voxel_material").reshape(60, 96, 96), ph.materials.transpose(2, 1, 0))
+        want = np.array([float("%.6f" % d) for d in np.unique(ph.densities)], dtype=np.float32)
+        assert set(np.unique(eng.table("voxel_density")).tolist()) == set(want.tolist())
