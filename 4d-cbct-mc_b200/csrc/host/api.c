@@ -227,7 +227,7 @@ typedef struct scan_shared {
   pthread_cond_t cv;
   int* done;       /* per projection: 0 pending, 1 done, 2 skipped, <0 error */
   double* seconds; /* per projection */
-  int hpt, blocks;
+  int hpt, blocks, write_raw;
   int* seeds;
 } scan_shared;
 
@@ -285,7 +285,8 @@ static void* scan_thread(void* arg) {
         launched = 1;
     }
     if (prev >= 0) { /* overlapped with the kernel just launched */
-      const int rc = mcgpu_write_projection_ascii(ctx, prev, image[cur ^ 1], prev_dt);
+      int rc = mcgpu_write_projection_ascii(ctx, prev, image[cur ^ 1], prev_dt);
+      if (rc == MCGPU_OK && sh->write_raw) rc = mcgpu_write_projection_raw(ctx, prev, image[cur ^ 1]);
       if (rc != MCGPU_OK) snprintf(w->err, sizeof w->err, "%s", ctx->err);
       scan_publish(sh, prev, rc == MCGPU_OK ? 1 : rc, prev_dt);
       if (rc != MCGPU_OK) failed = 1;
@@ -303,7 +304,8 @@ static void* scan_thread(void* arg) {
     }
   }
   if (prev >= 0) {
-    const int rc = mcgpu_write_projection_ascii(ctx, prev, image[cur ^ 1], prev_dt);
+    int rc = mcgpu_write_projection_ascii(ctx, prev, image[cur ^ 1], prev_dt);
+    if (rc == MCGPU_OK && sh->write_raw) rc = mcgpu_write_projection_raw(ctx, prev, image[cur ^ 1]);
     if (rc != MCGPU_OK) snprintf(w->err, sizeof w->err, "%s", ctx->err);
     scan_publish(sh, prev, rc == MCGPU_OK ? 1 : rc, prev_dt);
   }
@@ -330,6 +332,7 @@ int mcgpu_run_all(mcgpu_ctx* ctx, mcgpu_progress_cb cb, void* user) {
       if ((rc = mcgpu_run_projection(ctx, p, image)) != MCGPU_OK) break;
       dt = now_s() - t0;
       if ((rc = mcgpu_write_projection_ascii(ctx, p, image, dt)) != MCGPU_OK) break;
+      if (getenv("MCGPU_WRITE_RAW") && atoi(getenv("MCGPU_WRITE_RAW")) != 0 && (rc = mcgpu_write_projection_raw(ctx, p, image)) != MCGPU_OK) break;
       if (cb) cb(p, P, dt, user);
     }
     free(image);
@@ -345,6 +348,7 @@ int mcgpu_run_all(mcgpu_ctx* ctx, mcgpu_progress_cb cb, void* user) {
     unsigned long long launched;
     memset(&sh, 0, sizeof sh);
     sh.ctx = ctx;
+    sh.write_raw = getenv("MCGPU_WRITE_RAW") && atoi(getenv("MCGPU_WRITE_RAW")) != 0;
     sh.done = (int*)calloc((size_t)P, sizeof(int));
     sh.seconds = (double*)calloc((size_t)P, sizeof(double));
     sh.seeds = (int*)calloc((size_t)P, sizeof(int));

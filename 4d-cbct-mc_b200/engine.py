@@ -52,6 +52,7 @@ _SIGS = {
     "mcgpu_last_kernel_ms": (C.c_double, [C.c_void_p]),
     "mcgpu_run_all": (C.c_int, [C.c_void_p, PROGRESS_CB, C.c_void_p]),
     "mcgpu_write_projection_ascii": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_double]),
+    "mcgpu_write_projection_raw": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "mcgpu_projection_filename": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_size_t]),
     "mcgpu_reset_dose": (C.c_int, [C.c_void_p]),
     "mcgpu_get_dose": (C.c_longlong, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t]),
@@ -212,6 +213,10 @@ class Engine:
     def run_all(self, progress: Callable[[int, int, float], None] | None = None):
         cb = PROGRESS_CB((lambda p, n, s, u: progress(p, n, s)) if progress else (lambda p, n, s, u: None))
         self._check(_lib.mcgpu_run_all(self._h, cb, None))
+
+    def write_projection_raw(self, p: int, image: np.ndarray):
+        img = np.ascontiguousarray(image, dtype=np.uint64)
+        self._check(_lib.mcgpu_write_projection_raw(self._h, p, img.ctypes.data))
 
     def reset_dose(self):
         self._check(_lib.mcgpu_reset_dose(self._h))

@@ -235,6 +235,12 @@ def read_projection(path: Path, n_pixels: tuple[int, int]) -> np.ndarray:
     return data.reshape(nz, nx, 4).transpose(2, 0, 1).copy()
 
 
+def read_projection_raw(path: Path, n_pixels: tuple[int, int]) -> np.ndarray:
+    """Binary side-file (mcgpu_write_projection_raw): float32 [4, Nz, Nx], same values as the ASCII columns."""
+    nx, nz = n_pixels
+    return np.fromfile(path, dtype="<f4").reshape(4, nz, nx)
+
+
 def projection_counts(values: np.ndarray, n_pixels: tuple[int, int], detector_size_cm: tuple[float, float],
                       total_histories: int) -> np.ndarray:
     """Invert report_image's normalisation (MC-GPU_v1.3.cu:2860-2879) to recover the

@@ -127,6 +127,10 @@ int mcgpu_run_all(mcgpu_ctx* ctx, mcgpu_progress_cb cb, void* user);
 
 /* report_image (H:2783-2953): '<base>_%010.6fdeg' ASCII file, byte-compatible format. */
 int mcgpu_write_projection_ascii(mcgpu_ctx* ctx, int p, const uint64_t* image, double seconds);
+/* Optional binary side-file '<base>_%010.6fdeg.raw': little-endian float32 [4][Nz][Nx], same values as the
+ * ASCII columns (the reference's own .raw writer is commented out, H:2911-2949).  mcgpu_run_all writes it
+ * next to every ASCII file when the environment has MCGPU_WRITE_RAW=1. */
+int mcgpu_write_projection_raw(mcgpu_ctx* ctx, int p, const uint64_t* image);
 /* Name report_image gives the file of projection p; returns strlen or <0. */
 int mcgpu_projection_filename(const mcgpu_ctx* ctx, int p, char* out, size_t out_len);
 

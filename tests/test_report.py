@@ -95,3 +95,20 @@ def test_reader_round_trip(written, pkg, tmp_path):
     vals = pkg.mcio.read_projection(f, cfg.n_detector_pixels)
     det_cm = (round(cfg.detector_size[0] / 10, 6), round(cfg.detector_size[1] / 10, 6))
     assert np.array_equal(pkg.mcio.projection_counts(vals, cfg.n_detector_pixels, det_cm, launched), counts)
+
+
+def test_binary_side_file_matches_ascii(pkg, cases, tmp_path):
+    inp, cfg, _ = cases["water_p1"]
+    counts = np.load(GOLDEN / "water_p1.npz")["projection_000.000000deg"]
+    text = open(inp).read().replace(str(Path(inp).parent) + "/projection", str(tmp_path / "projection"))
+    f = tmp_path / "w.in"
+    f.write_text(text)
+    with pkg.engine.Engine() as eng:
+        eng.load_input(f)
+        eng.write_projection(0, counts, 0.0)
+        eng.write_projection_raw(0, counts)
+        name = eng.projection_filename(0)
+    raw = pkg.mcio.read_projection_raw(name + ".raw", cfg.n_detector_pixels)
+    txt = pkg.mcio.read_projection(name, cfg.n_detector_pixels)
+    assert raw.shape == txt.shape == (4, cfg.n_detector_pixels[1], cfg.n_detector_pixels[0])
+    assert np.allclose(raw, txt, rtol=1e-6, atol=1e-8) and raw.sum() > 0
