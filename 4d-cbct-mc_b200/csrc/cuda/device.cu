@@ -92,7 +92,8 @@ extern "C" int mcgpu_dev_upload(struct mcgpu_device* d, const mcgpu_scene* s, co
   d->image_words = (size_t)4 * npix_total;
   if (upload(&d->d_image, NULL, sizeof(unsigned long long) * d->image_words, err, errlen)) return -1;
   CK(cudaMemset(d->d_image, 0, sizeof(unsigned long long) * d->image_words));
-  CK(cudaMalloc((void**)&d->d_stream_counter, sizeof(unsigned long long)));
+  CK(cudaMalloc((void**)&d->d_stream_counter, 2 * sizeof(unsigned long long)));
+  CK(cudaMemset(d->d_stream_counter, 0, 2 * sizeof(unsigned long long)));
   d->dose_roi_voxels = 0;
   if (s->tally_material_dose) {
     CK(cudaMalloc((void**)&d->d_materials_dose, sizeof(unsigned long long) * 2 * MCGPU_MAX_MATERIALS));
@@ -106,9 +107,11 @@ extern "C" int mcgpu_dev_upload(struct mcgpu_device* d, const mcgpu_scene* s, co
   {  // tuning / A-B switches (documented in DESIGN.md); the defaults are the product path
     const char* k = getenv("MCGPU_KERNEL");
     const char* t = getenv("MCGPU_W_THRESHOLD");
-    d->kernel_generation = (k && atoi(k) == 1) ? 1 : 2;
+    d->kernel_generation = (k && atoi(k) == 1) ? 1 : (k && atoi(k) == 3) ? 3 : 2;
     if (getenv("MCGPU_FAST_MATH")) d->fast_math = atoi(getenv("MCGPU_FAST_MATH")) != 0;  // A/B convenience; the API is mcgpu_set_fast_math
-    d->w_threshold = t ? atoi(t) : 8;
+    d->w_threshold = t ? atoi(t) : (d->kernel_generation == 3 ? 16 : 8);
+    d->wf_roles = getenv("MCGPU_WF_ROLES") ? atoi(getenv("MCGPU_WF_ROLES")) & 31 : 0;
+    d->wf_block = (getenv("MCGPU_WF_BLOCK") && atoi(getenv("MCGPU_WF_BLOCK")) == 512) ? 512 : 1024;
     if (d->w_threshold < 1) d->w_threshold = 1;
     if (d->w_threshold > 32) d->w_threshold = 32;
   }
@@ -160,6 +163,14 @@ extern "C" int mcgpu_dev_sync(struct mcgpu_device* d, float* kernel_ms, char* er
   if (kernel_ms) {
     *kernel_ms = 0.f;
     if (d->timed) CK(cudaEventElapsedTime(kernel_ms, d->ev0, d->ev1));
+  }
+  if (d->kernel_generation == 3 && d->d_stream_counter) {  // the wavefront kernel reports a lost context instead of hanging
+    unsigned long long flag = 0;
+    CK(cudaMemcpy(&flag, d->d_stream_counter + 1, sizeof flag, cudaMemcpyDeviceToHost));
+    if (flag) {
+      snprintf(err, errlen, "device %d: wavefront transport kernel watchdog fired (code %llu)", d->ordinal, flag & 0xffffffffull);
+      return -1;
+    }
   }
   return 0;
 }

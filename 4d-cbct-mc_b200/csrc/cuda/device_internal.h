@@ -8,6 +8,7 @@
 
 #include "transport.cuh"
 #include "regroup.cuh"
+#include "wavefront.cuh"
 
 #define CK(call)                                                                                    \
   do {                                                                                              \
@@ -40,9 +41,11 @@ struct mcgpu_device {
   unsigned long long* d_materials_dose;  // [25][2] or NULL
   unsigned long long* d_voxels_edep;     // [roi][2] or NULL
   long long dose_roi_voxels;
-  unsigned long long* d_stream_counter;  // next stream of the running launch (regrouping kernel)
-  int kernel_generation;                 // 2 = regrouping persistent warps (default), 1 = one thread per stream (reference structure, for A/B)
+  unsigned long long* d_stream_counter;  // [0] next stream of the running launch (persistent kernels), [1] kernel error flag (wavefront)
+  int kernel_generation;                 // 2 = regrouping persistent warps (default), 3 = block wavefront with work queues, 1 = one thread per stream (reference structure, for A/B)
   int w_threshold;
+  int wf_block;                          // wavefront kernel: threads per CTA (512: two CTAs per SM, 1024: one)
+  int wf_roles;                          // wavefront kernel: bit s set = warps of SM sub-partition s prefer tracking batches
   int fast_math;                         // 0 = bit-exact arithmetic (default), 1 = the reference's shipped -use_fast_math flags
   uint64_t* h_stage;
   int timed;

@@ -150,11 +150,46 @@ extern "C" int MCGPU_LAUNCH_NAME(struct mcgpu_device* d, const mcgpu_view* view,
                                                                           l->histories_per_thread, l->seed_input, g1, g2,                \
                                                                           d->d_stream_counter, d->w_threshold);                          \
   }
+#define LAUNCH_WAVEFRONT_D(B, DOSE_, ROT_)                                                                                                \
+  {                                                                                                                                      \
+    const int pal = (B == 4 || B == 8) ? d->scene.palette_size : 0;                                                                      \
+    const int wblock = d->wf_block;                                                                                                      \
+    int smem_sm = 0, per_sm = MCGPU_WF_MAX_BLOCK / wblock, pool = 0;                                                                     \
+    CK(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, d->ordinal));                                       \
+    const size_t fixed = wavefront_layout(d->scene.num_slots, d->scene.max_shells, pal, 0, wblock / 32).total;                           \
+    for (; per_sm >= 1; per_sm--) {                                                                                                      \
+      const long long budget = (long long)smem_sm / per_sm - 1024 - (long long)fixed;                                                    \
+      pool = budget > 0 ? (int)(budget / (long long)(sizeof(float) * MCGPU_WF_FIELDS)) & ~31 : 0;                                        \
+      if (pool > 2 * wblock) pool = 2 * wblock;                                                                                          \
+      if (pool > MCGPU_WF_MAX_POOL) pool = MCGPU_WF_MAX_POOL;                                                                            \
+      if (pool >= wblock) break;                                                                                                         \
+    }                                                                                                                                    \
+    if (pool < 64) {                                                                                                                     \
+      snprintf(err, errlen, "device %d: not enough shared memory for the wavefront kernel", d->ordinal);                                 \
+      return -1;                                                                                                                         \
+    }                                                                                                                                    \
+    const size_t wsmem = wavefront_layout(d->scene.num_slots, d->scene.max_shells, pal, pool, wblock / 32).total;                        \
+    CK(cudaFuncSetAttribute(transport_wavefront<B, DOSE_, ROT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));              \
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, transport_wavefront<B, DOSE_, ROT_>, wblock, wsmem));                      \
+    long long pgrid = (long long)d->sm_count * (per_sm > 0 ? per_sm : 1);                                                                \
+    const long long useful = (n_streams + pool - 1) / pool;                                                                              \
+    if (pgrid > useful) pgrid = useful;                                                                                                  \
+    CK(cudaMemsetAsync(d->d_stream_counter, 0, 2 * sizeof(unsigned long long), d->stream));                                              \
+    transport_wavefront<B, DOSE_, ROT_><<<(unsigned)pgrid, wblock, wsmem, d->stream>>>(                                                  \
+        d->scene, *view, l->stream_begin, l->stream_end, l->histories_per_thread, l->seed_input, g1, g2, d->d_stream_counter,            \
+        d->w_threshold, pool, pal, d->wf_roles, reinterpret_cast<int*>(d->d_stream_counter + 1));                                        \
+  }
 #define LAUNCH(B)                                                                                                                        \
   if (d->kernel_generation == 1) {                                                                                                       \
     CK(cudaFuncSetAttribute(transport_streams<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                              \
     transport_streams<B><<<(unsigned)grid, block, smem, d->stream>>>(d->scene, *view, l->stream_begin, l->stream_end, l->histories_per_thread, \
                                                                      l->seed_input, g1, g2);                                            \
+  } else if (d->kernel_generation == 3) {                                                                                                \
+    if (d->scene.materials_dose || d->scene.voxels_edep) {                                                                               \
+      LAUNCH_WAVEFRONT_D(B, true, -1)                                                                                                    \
+    } else {                                                                                                                             \
+      if (view->rotation_flag == 1) { LAUNCH_WAVEFRONT_D(B, false, 1) } else { LAUNCH_WAVEFRONT_D(B, false, 0) }                         \
+    }                                                                                                                                    \
   } else {                                                                                                                               \
     smem += sizeof(float) * (MCGPU_REGROUP_BLOCK / 32) * MCGPU_SCRATCH_ROWS * regroup_scratch_stride(d->scene.max_shells) + 8;           \
     if (d->scene.materials_dose || d->scene.voxels_edep) {                                                                               \
@@ -170,6 +205,7 @@ extern "C" int MCGPU_LAUNCH_NAME(struct mcgpu_device* d, const mcgpu_view* view,
       default: LAUNCH(64) break;
     }
 #undef LAUNCH
+#undef LAUNCH_WAVEFRONT_D
 #undef LAUNCH_REGROUP_D
     CK(cudaGetLastError());
   }

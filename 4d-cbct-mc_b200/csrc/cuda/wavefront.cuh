@@ -1,0 +1,426 @@
+// Transport kernel, generation 3: block-level wavefront with typed work queues.
+//
+// Why: generation 2 (regroup.cuh) regroups the 32 photons a warp owns, so at any time only ~half
+// of them wait for the same event: 14.5-16 of 32 lanes are active per issued instruction
+// (profiles/r01_final_*_ncu_summary.txt) and the serial parts of Compton run at 4-5 lanes.  The
+// kernel is issue-bound, so idle lanes are the loss that is left.
+//
+// How: a CTA of 16 warps owns a POOL of photon contexts in shared memory (2 per thread; a context
+// = one RANECU stream and the photon it is tracking, 12 words) and four queues of context ids, one
+// per kind of work:
+//   Q_W  delta-tracking steps                       Q_N  tally / next stream / next history (source)
+//   Q_C  Compton (S0 for fresh events + one tau trial)   Q_R  Rayleigh
+// A warp repeatedly pops up to 32 ids from ONE queue, loads those contexts into registers, runs
+// that kind of work for all lanes (the same code as generation 2's phases), stores the contexts and
+// pushes every id to the queue of its new state.  Because a queue collects the photons of 512
+// threads, batches are (nearly) full whatever the event mix.  A context is held by one warp at a
+// time and its stream is advanced strictly in order, so every float of every trajectory and hence
+// every integer tally is identical to generations 1 and 2 and to the reference (tested).
+//
+// Queues are rings of 16-bit ids in shared memory: `tail` is reserved with one warp-aggregated
+// atomicAdd per push, entries are published individually (an entry is EMPTY until written),
+// `avail` counts published entries and is claimed with atomicCAS by the popping warp, `head` gives
+// it its ring positions.  No locks; the only waits are on an entry that is reserved but not yet
+// written, and they are bounded (a watchdog raises the launch's error flag instead of hanging).
+#pragma once
+#include "regroup.cuh"
+
+namespace MCGPU_NS {
+
+#define MCGPU_WF_MAX_BLOCK 1024
+#define MCGPU_WF_RING 2048  // entries per queue ring; >= pool size, power of two
+#define MCGPU_WF_EMPTY 0xffffu
+#define MCGPU_WF_FIELDS 12
+#define MCGPU_WF_MAX_POOL 2048
+
+enum WfQueue : int { Q_W = 0, Q_N = 1, Q_C = 2, Q_R = 3, Q_COUNT = 4 };
+enum WfField : int { F_X = 0, F_Y, F_Z, F_U, F_V, F_W, F_E, F_S1, F_S2, F_S0, F_HIST, F_META };
+
+struct WfControl {
+  unsigned head[Q_COUNT];
+  unsigned tail[Q_COUNT];
+  int avail[Q_COUNT];
+  int live;          // contexts that still have work (not finished)
+  int active_warps;  // warps that have not retired
+  int phase;         // queue the CTA is draining (sticky scheduling)
+  int pad[1];
+};
+
+// shared-memory carve-up, used by the kernel and by the host to size the launch
+struct WfLayout {
+  size_t shells, scratch, palette, control, rings, pool, total;
+  int stride;
+};
+__host__ __device__ inline WfLayout wavefront_layout(int num_slots, int max_shells, int palette_entries, int pool_size, int warps) {
+  WfLayout L;
+  L.stride = regroup_scratch_stride(max_shells);
+  L.shells = (sizeof(SharedTables) + 15) & ~size_t(15);
+  L.scratch = L.shells + sizeof(float4) * num_slots * MCGPU_MAX_SHELLS;
+  L.palette = (L.scratch + sizeof(float) * warps * MCGPU_SCRATCH_ROWS * L.stride + 15) & ~size_t(15);
+  L.control = (L.palette + sizeof(float2) * palette_entries + 15) & ~size_t(15);
+  L.rings = L.control + sizeof(WfControl);
+  L.pool = (L.rings + sizeof(unsigned short) * Q_COUNT * MCGPU_WF_RING + 15) & ~size_t(15);
+  L.total = L.pool + sizeof(float) * MCGPU_WF_FIELDS * pool_size;
+  return L;
+}
+
+__device__ __forceinline__ int wf_pack_meta(int state, int scatter_state, int slot) { return state | (scatter_state << 3) | (slot << 8); }
+
+template <int BITS, bool DOSE, int ROT>
+__global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
+    transport_wavefront(const SceneDev sc, const __grid_constant__ mcgpu_view vw, long long stream_begin, long long stream_end, int histories_per_thread, int seed_input,
+                        int g1, int g2, unsigned long long* __restrict__ stream_counter, int w_threshold, int pool_size, int palette_entries, int w_roles, int* __restrict__ error_flag) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const WfLayout L = wavefront_layout(sc.num_slots, sc.max_shells, palette_entries, pool_size, (int)(blockDim.x >> 5));
+  SharedTables& st = *reinterpret_cast<SharedTables*>(smem_raw);
+  float4* sh_shells = reinterpret_cast<float4*>(smem_raw + L.shells);
+  float* sh_scratch = reinterpret_cast<float*>(smem_raw + L.scratch);
+  float2* sh_palette = reinterpret_cast<float2*>(smem_raw + L.palette);
+  WfControl* ctl = reinterpret_cast<WfControl*>(smem_raw + L.control);
+  volatile unsigned short* rings = reinterpret_cast<volatile unsigned short*>(smem_raw + L.rings);
+  float* pool = reinterpret_cast<float*>(smem_raw + L.pool);
+  int* pool_i = reinterpret_cast<int*>(pool);
+  const int stride = L.stride;
+
+  for (int i = threadIdx.x; i < MCGPU_MAX_ENERGY_BINS; i += blockDim.x) {
+    st.espc[i] = sc.spectrum->espc[i];
+    st.cutoff[i] = sc.spectrum->cutoff[i];
+    st.alias[i] = sc.spectrum->alias[i];
+  }
+  if (threadIdx.x == 0) st.num_bins = sc.spectrum->num_bins;
+  for (int i = threadIdx.x; i < sc.num_slots * MCGPU_MAX_SHELLS; i += blockDim.x) sh_shells[i] = sc.cmp_shells[i];
+  if (BITS == 4 || BITS == 8)
+    for (int i = threadIdx.x; i < sc.palette_size; i += blockDim.x) sh_palette[i] = sc.palette[i];
+  // every context starts in Q_N asking for a stream
+  for (int i = threadIdx.x; i < Q_COUNT * MCGPU_WF_RING; i += blockDim.x) rings[i] = MCGPU_WF_EMPTY;
+  __syncthreads();
+  for (int i = threadIdx.x; i < pool_size; i += blockDim.x) {
+    rings[Q_N * MCGPU_WF_RING + i] = (unsigned short)i;
+    pool_i[F_META * pool_size + i] = wf_pack_meta(ST_I, 0, 0);
+    pool_i[F_HIST * pool_size + i] = 0;
+    pool_i[F_S1 * pool_size + i] = 1;
+    pool_i[F_S2 * pool_size + i] = 1;
+  }
+  if (threadIdx.x == 0) {
+    for (int t = 0; t < Q_COUNT; t++) ctl->head[t] = 0u, ctl->tail[t] = 0u, ctl->avail[t] = 0;
+    ctl->tail[Q_N] = (unsigned)pool_size;
+    ctl->avail[Q_N] = pool_size;
+    ctl->live = pool_size;
+    ctl->active_warps = (int)(blockDim.x >> 5);
+    ctl->phase = Q_N;
+  }
+  __syncthreads();
+
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  float* wbuf = sh_scratch + (threadIdx.x >> 5) * MCGPU_SCRATCH_ROWS * stride;
+  const long long n_streams = stream_end - stream_begin;
+  volatile int* v_avail = ctl->avail;
+  volatile int* v_live = &ctl->live;
+  volatile int* v_phase = &ctl->phase;
+  const bool sticky = (w_roles & 16) != 0;
+  const bool prefer_w = (w_roles >> ((threadIdx.x >> 5) & 3)) & 1;  // warps of this SM sub-partition prefer tracking batches
+  const bool event_warp = (w_roles & 15) != 0 && !prefer_w;
+
+#define PF(f) pool[(f) * pool_size + pid]
+#define PI(f) pool_i[(f) * pool_size + pid]
+
+  for (;;) {
+    // ------------------------------------------------------------------ acquire a batch: up to 32 ids of one queue
+    int q = 0, n = 0;
+    unsigned pos = 0;
+    if (lane == 0) {
+      int idle = 0;
+      for (;;) {
+        const int a0 = v_avail[0], a1 = v_avail[1], a2 = v_avail[2], a3 = v_avail[3];
+        int best = -1, a = 0;
+        if (sticky) {  // keep draining the queue the CTA is working on: one kind of code at a time in the SM's instruction cache
+          const int ph = *v_phase;
+          const int ap = ph == Q_W ? a0 : ph == Q_N ? a1 : ph == Q_C ? a2 : a3;
+          if (ap >= 32) best = ph, a = ap;
+          else {
+            if (a0 > a) best = Q_W, a = a0;
+            if (a1 > a) best = Q_N, a = a1;
+            if (a2 > a) best = Q_C, a = a2;
+            if (a3 > a) best = Q_R, a = a3;
+            if (best >= 0 && best != ph) *v_phase = best;
+          }
+        } else if (prefer_w && a0 >= 32) best = Q_W, a = a0;  // tracking warps stay in the tracking loop (instruction-cache locality)
+        else if (a2 >= 32) best = Q_C, a = a2;   // full batches first, rarest work first
+        else if (a3 >= 32) best = Q_R, a = a3;
+        else if (a1 >= 32) best = Q_N, a = a1;
+        else if (event_warp && (a1 >= 16 || a2 >= 16)) {  // event warps take half-full event batches before they track
+          if (a2 > a1) best = Q_C, a = a2;
+          else best = Q_N, a = a1;
+        } else if (a0 >= 32) best = Q_W, a = a0;
+        else {                                   // nothing full: the fullest queue
+          if (a0 > a) best = Q_W, a = a0;
+          if (a1 > a) best = Q_N, a = a1;
+          if (a2 > a) best = Q_C, a = a2;
+          if (a3 > a) best = Q_R, a = a3;
+        }
+        if (best < 0) {
+          if (*v_live == 0) break;  // all streams of this CTA are done
+          if (++idle > 4096) {      // ~1 ms without work: this warp retires, the others finish the tail
+            if (atomicSub(&ctl->active_warps, 1) > 1) break;
+            atomicAdd(&ctl->active_warps, 1);
+            if (idle > (1 << 22)) {  // last warp, contexts alive but nowhere: a context was lost
+              atomicExch(error_flag, 1);
+              break;
+            }
+          }
+          __nanosleep(200);
+          continue;
+        }
+        const int take = a < 32 ? a : 32;
+        if (atomicCAS(&ctl->avail[best], a, a - take) == a) {
+          q = best, n = take;
+          pos = atomicAdd(&ctl->head[best], (unsigned)take);
+          break;
+        }
+      }
+    }
+    q = __shfl_sync(MCGPU_FULL_MASK, q, 0);
+    n = __shfl_sync(MCGPU_FULL_MASK, n, 0);
+    pos = __shfl_sync(MCGPU_FULL_MASK, pos, 0);
+    if (n <= 0) break;
+
+    bool act = (int)lane < n;
+    int pid = 0;
+    if (act) {
+      volatile unsigned short* e = rings + q * MCGPU_WF_RING + ((pos + lane) & (MCGPU_WF_RING - 1));
+      unsigned v;
+      int guard = 0;
+      while ((v = *e) == MCGPU_WF_EMPTY) {
+        if (++guard > (1 << 24)) break;
+      }
+      if (v == MCGPU_WF_EMPTY) {
+        atomicExch(error_flag, 2);
+        act = false;
+      } else {
+        *e = MCGPU_WF_EMPTY;
+        pid = (int)v;
+      }
+    }
+    __syncwarp();
+    __threadfence_block();
+
+    Photon p;
+    Ranecu rng;
+    int state = ST_F, slot = 0, scatter_state = 0;
+    p.x = p.y = p.z = p.u = p.v = p.w = p.E = 0.f;
+    rng.s1 = rng.s2 = 1;
+    if (act) {
+      const int meta = PI(F_META);
+      state = meta & 7, scatter_state = (meta >> 3) & 3, slot = meta >> 8;
+      rng.s1 = PI(F_S1), rng.s2 = PI(F_S2);
+    }
+
+    if (q == Q_W) {
+      // ---------------------------------------------------------------- W: delta-tracking steps (K:249-279)
+      mcgpu_mfp_record rec;
+      rec.ax = rec.ay = rec.az = rec.bx = rec.by = rec.bz = rec.pmax_next = rec.pad = 0.f;
+      float mfp_woodcock = 0.f;
+      int index = 0, slot_old = -1;
+      if (act) {
+        p.x = PF(F_X), p.y = PF(F_Y), p.z = PF(F_Z), p.u = PF(F_U), p.v = PF(F_V), p.w = PF(F_W), p.E = PF(F_E);
+        index = __float2int_rd((p.E - sc.e0) * sc.ide);
+        const float2 w = __ldg(&sc.woodcock[index]);
+        mfp_woodcock = w.x + p.E * w.y;
+      }
+      const int thr = min(w_threshold, (n + 1) >> 1);
+      do {
+        if (state == ST_W) {
+          const float step = -(mfp_woodcock)*logf(rng.uniform());
+          p.x += step * p.u;
+          p.y += step * p.v;
+          p.z += step * p.w;
+          const int absvox = locate_voxel(sc, p);
+          if (absvox < 0) {
+            state = ST_T;  // escaped with index > -1: goes to the detector
+          } else {
+            const float2 md = fetch_voxel<BITS>(sc, sh_palette, absvox);
+            slot = __float_as_int(md.y);
+            if (slot != slot_old) {
+              const float4* r4 = reinterpret_cast<const float4*>(&sc.mfp[(size_t)index * sc.num_slots + slot]);
+              const float4 lo = __ldg(r4), hi = __ldg(r4 + 1);
+              rec.ax = lo.x, rec.ay = lo.y, rec.az = lo.z, rec.bx = lo.w;
+              rec.by = hi.x, rec.bz = hi.y, rec.pmax_next = hi.z;
+              slot_old = slot;
+            }
+            const float mfp_density = mfp_woodcock * md.x;
+            float prob = 1.0f - mfp_density * (rec.ax + p.E * rec.bx);
+            const float randno = rng.uniform();
+            if (!(randno < prob)) {  // real interaction: classify now (K:289-353), sample in a batch of its kind
+              prob += mfp_density * (rec.ay + p.E * rec.by);
+              if (randno < prob) {
+                state = ST_C;
+              } else {
+                prob += mfp_density * (rec.az + p.E * rec.bz);
+                state = (randno < prob) ? ST_R : ST_N;  // else: photoelectric absorption, history over
+                if (DOSE && state == ST_N) deposit_energy(sc, p, slot, p.E);  // K:351
+              }
+            }
+          }
+        }
+      } while (__popc(__ballot_sync(MCGPU_FULL_MASK, state == ST_W)) >= thr);
+      if (act) PF(F_X) = p.x, PF(F_Y) = p.y, PF(F_Z) = p.z;
+    } else if (q == Q_N) {
+      // ---------------------------------------------------------------- T / I / N: tally, next stream, next history
+      int hist_left = 0;
+      if (act) {
+        hist_left = PI(F_HIST);
+        p.x = PF(F_X), p.y = PF(F_Y), p.z = PF(F_Z), p.u = PF(F_U), p.v = PF(F_V), p.w = PF(F_W), p.E = PF(F_E);
+      }
+      const int thr = min(16, (n + 1) >> 1);
+      for (;;) {
+        if (state == ST_T) {  // K:377-381
+          tally_photon<ROT>(sc, vw, p, scatter_state);
+          state = ST_N;
+        }
+        {  // next stream of the launch (K:198)
+          const bool want = (state == ST_N && hist_left == 0) || state == ST_I;
+          const unsigned m_i = __ballot_sync(MCGPU_FULL_MASK, want);
+          if (m_i) {
+            unsigned long long base = 0;
+            const int leader = __ffs(m_i) - 1;
+            if ((int)lane == leader) base = atomicAdd(stream_counter, (unsigned long long)__popc(m_i));
+            base = __shfl_sync(MCGPU_FULL_MASK, base, leader);
+            if (want) {
+              const long long s = (long long)base + __popc(m_i & lt_mask);
+              if (s < n_streams) {
+                ranecu_init(rng, stream_begin + s, seed_input, g1, g2);
+                hist_left = histories_per_thread;
+                state = ST_N;
+              } else {
+                state = ST_F;
+              }
+            }
+          }
+        }
+        if (state == ST_N) {  // K:210-234
+          hist_left--;
+          const bool enters = emit_photon<ROT>(sc, vw, st, rng, p);
+          scatter_state = 0;
+          state = enters ? ST_W : ST_T;  // a primary that misses the voxels can still hit the detector (K:240-241)
+        }
+        if (__popc(__ballot_sync(MCGPU_FULL_MASK, state == ST_T)) < thr) break;
+      }
+      if (act) {
+        PF(F_X) = p.x, PF(F_Y) = p.y, PF(F_Z) = p.z, PF(F_U) = p.u, PF(F_V) = p.v, PF(F_W) = p.w, PF(F_E) = p.E;
+        PI(F_HIST) = hist_left;
+      }
+    } else {
+      // ---------------------------------------------------------------- C / CT / R: one scattering step
+      float s0 = 0.f;
+      if (act) {
+        p.u = PF(F_U), p.v = PF(F_V), p.w = PF(F_W), p.E = PF(F_E);
+        if (DOSE) p.x = PF(F_X), p.y = PF(F_Y), p.z = PF(F_Z);
+        s0 = PF(F_S0);
+      }
+      double costh = 0.0;
+      bool deflect_pending = false;
+      if (q == Q_C) {
+        unsigned todo = __ballot_sync(MCGPU_FULL_MASK, act);
+        const unsigned fresh = __ballot_sync(MCGPU_FULL_MASK, state == ST_C);
+        while (todo) {
+          const unsigned m = limit_rows(todo);  // the scratch holds MCGPU_SCRATCH_ROWS photons
+          todo &= ~m;
+          const bool mine = (m >> lane) & 1u;
+          const unsigned m_c = m & fresh;
+          if (m_c) {  // S0 of fresh events (K:1315-1339)
+            coop_shell_terms(m_c, p.E, slot, 2.f, false, sh_shells, sc, wbuf, stride, lane);
+            if ((m_c >> lane) & 1u) {
+              s0 = compton_ordered_sum<false>(sc.cmp_noscco[slot], wbuf + __popc(m_c & lt_mask) * stride);
+              state = ST_CT;
+            }
+            __syncwarp();
+          }
+          {  // one tau trial per photon (K:1342-1403), rest of GCOa if accepted
+            const ComptonKin kin(p.E);
+            float tau = 1.f;
+            double cdt1 = 0.0;
+            if (mine) cdt1 = compton_propose_tau(kin, p.E, rng, tau);
+            coop_shell_terms(m, p.E, slot, (float)cdt1, true, sh_shells, sc, wbuf, stride, lane);
+            if (mine) {
+              const int nosc = sc.cmp_noscco[slot];
+              float* row = wbuf + __popc(m & lt_mask) * stride;
+              const float s = compton_ordered_sum<true>(nosc, row);
+              if (compton_accept(kin, s0, s, tau, rng)) {
+                const float e_before = p.E;
+                costh = compton_finish(p.E, s, tau, cdt1, sh_shells + slot * MCGPU_MAX_SHELLS, nosc, row, rng);
+                if (DOSE) deposit_energy(sc, p, slot, -1.0f * (p.E - e_before));  // K:296-301, 359
+                deflect_pending = true;
+              }
+            }
+            __syncwarp();
+          }
+        }
+      } else if (act) {  // Rayleigh (K:329-347); pmax of the bin above, same table entry the tracking step used
+        const int index = __float2int_rd((p.E - sc.e0) * sc.ide);
+        const float pmax_next = __ldg(&sc.mfp[(size_t)index * sc.num_slots + slot].pmax_next);
+        costh = sample_rayleigh(sc, p.E, slot, pmax_next, rng);
+        deflect_pending = true;
+      }
+      if (deflect_pending) {  // new direction for both kinds of scattering (K:299, K:339)
+        deflect(p, costh, 6.28318530717958647693 * rng.uniform_d());
+        if (state == ST_R) {
+          scatter_state = (scatter_state == 0) ? 2 : 3;
+          state = ST_W;
+        } else {
+          const int index = __float2int_rd((p.E - sc.e0) * sc.ide);
+          if (index > -1) {
+            scatter_state = (scatter_state == 0) ? 1 : 3;
+            state = ST_W;
+          } else {
+            state = ST_N;  // below the tabulated energies: absorbed (K:311, K:372)
+          }
+        }
+      }
+      if (act) {
+        PF(F_U) = p.u, PF(F_V) = p.v, PF(F_W) = p.w, PF(F_E) = p.E;
+        PF(F_S0) = s0;
+      }
+    }
+
+    // ------------------------------------------------------------------ store what every kind changes, hand the ids on
+    if (act) {
+      PI(F_S1) = rng.s1, PI(F_S2) = rng.s2;
+      PI(F_META) = wf_pack_meta(state, scatter_state, slot);
+    }
+    __threadfence_block();
+    const int nq = !act || state == ST_F ? -1 : state == ST_W ? Q_W : (state == ST_C || state == ST_CT) ? Q_C : state == ST_R ? Q_R : Q_N;
+#pragma unroll 1
+    for (int t = 0; t < Q_COUNT; t++) {
+      const unsigned m = __ballot_sync(MCGPU_FULL_MASK, nq == t);
+      if (m) {
+        const int leader = __ffs(m) - 1;
+        unsigned base = 0;
+        if ((int)lane == leader) base = atomicAdd(&ctl->tail[t], (unsigned)__popc(m));
+        base = __shfl_sync(MCGPU_FULL_MASK, base, leader);
+        if (nq == t) {
+          volatile unsigned short* e = rings + t * MCGPU_WF_RING + ((base + __popc(m & lt_mask)) & (MCGPU_WF_RING - 1));
+          int guard = 0;
+          while (*e != MCGPU_WF_EMPTY) {  // its previous occupant is being taken by another warp right now
+            if (++guard > (1 << 24)) {
+              atomicExch(error_flag, 3);
+              break;
+            }
+          }
+          *e = (unsigned short)pid;
+        }
+        __threadfence_block();
+        __syncwarp();
+        if ((int)lane == leader) atomicAdd(&ctl->avail[t], __popc(m));
+      }
+    }
+    {
+      const unsigned m_f = __ballot_sync(MCGPU_FULL_MASK, act && state == ST_F);
+      if (m_f && lane == 0) atomicSub(&ctl->live, __popc(m_f));
+    }
+  }
+#undef PF
+#undef PI
+}
+
+}  // namespace MCGPU_NS

@@ -12,12 +12,13 @@ There is no fallback of any kind: a missing library raises at import, and every 
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 from typing import Callable, Sequence
 
 import numpy as np
 
-_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libmcgpu_b200.so"
+_LIB_PATH = Path(os.environ.get("MCGPU_B200_LIB") or Path(__file__).resolve().parent / "lib" / "libmcgpu_b200.so")  # env: developer A/B builds only
 if not _LIB_PATH.exists():
     raise ImportError(f"{_LIB_PATH} is missing: run `make lib` (or __graft_entry__.build()); there is no CPU fallback")
 _lib = C.CDLL(str(_LIB_PATH))

@@ -19,7 +19,7 @@ NVFLAGS  := -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a \
 HOST_SRC := input.c geometry.c voxels.c tables.c ranecu_host.c report.c dose.c api.c
 HOST_OBJ := $(HOST_SRC:%.c=$(BUILD)/%.o)
 CUDA_OBJ := $(BUILD)/device.o $(BUILD)/launch_exact.o $(BUILD)/launch_fast.o
-CUDA_HDR := $(CUDADIR)/transport.cuh $(CUDADIR)/regroup.cuh $(CUDADIR)/scene_dev.h $(CUDADIR)/device_internal.h $(HOSTDIR)/mcgpu_host.h
+CUDA_HDR := $(CUDADIR)/transport.cuh $(CUDADIR)/regroup.cuh $(CUDADIR)/wavefront.cuh $(CUDADIR)/scene_dev.h $(CUDADIR)/device_internal.h $(HOSTDIR)/mcgpu_host.h
 
 all: lib exe oracle
 
@@ -39,12 +39,12 @@ $(BUILD)/device.o: $(CUDADIR)/device.cu $(CUDA_HDR)
 # the kernels, twice: bit-exact arithmetic (default path) and the reference's shipped fast-math flags (opt-in)
 $(BUILD)/launch_exact.o: $(CUDADIR)/launch.cu $(CUDA_HDR)
 	@mkdir -p $(BUILD)
-	$(NVCC) $(NVFLAGS) -fmad=false -Xptxas -v -c $< -o $@ 2> $(BUILD)/ptxas_exact.log || (cat $(BUILD)/ptxas_exact.log; false)
+	$(NVCC) $(NVFLAGS) -fmad=false $(XFLAGS) -Xptxas -v -c $< -o $@ 2> $(BUILD)/ptxas_exact.log || (cat $(BUILD)/ptxas_exact.log; false)
 	@grep -E "registers|spill" $(BUILD)/ptxas_exact.log | sort | uniq -c | head -20
 
 $(BUILD)/launch_fast.o: $(CUDADIR)/launch.cu $(CUDA_HDR)
 	@mkdir -p $(BUILD)
-	$(NVCC) $(NVFLAGS) -use_fast_math -DMCGPU_FAST_MATH -DMCGPU_NS=mcgpu_fast -Xptxas -v -c $< -o $@ 2> $(BUILD)/ptxas_fast.log || (cat $(BUILD)/ptxas_fast.log; false)
+	$(NVCC) $(NVFLAGS) -use_fast_math -DMCGPU_FAST_MATH -DMCGPU_NS=mcgpu_fast $(XFLAGS) -Xptxas -v -c $< -o $@ 2> $(BUILD)/ptxas_fast.log || (cat $(BUILD)/ptxas_fast.log; false)
 	@grep -E "registers|spill" $(BUILD)/ptxas_fast.log | sort | uniq -c | head -20
 
 $(LIBDIR)/libmcgpu_b200.so: $(HOST_OBJ) $(CUDA_OBJ)

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Kernel A/B and tuning sweep on the GPU box: histories/s of one projection for each workload and
-each (MCGPU_KERNEL, MCGPU_W_THRESHOLD) setting; every variant is also checked for bit-identical
+each (MCGPU_KERNEL, MCGPU_W_THRESHOLD) setting (--kernels=1,2,3 --thresholds=8 --t3=12,16,20); every variant is also checked for bit-identical
 tallies against the first one.  Usage: python tools/sweep.py [workloads...] [--hist N] [--thresholds a,b,c]"""
 import json
 import os
@@ -22,7 +22,7 @@ def main():
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
     opts = dict(a[2:].split("=") for a in sys.argv[1:] if a.startswith("--") and "=" in a)
     hist = int(opts.get("hist", 100_000_000))
-    thresholds = opts.get("thresholds", "8:8").split(",")  # w_threshold:min_blocks
+    thresholds = opts.get("thresholds", "8").split(",")  # w_threshold of the regrouping kernel
     kernels = [int(x) for x in opts.get("kernels", "1,2").split(",")]
     workloads = args or ["thorax", "catphan"]
     factories = {"thorax": pkg.phantoms.thorax, "catphan": pkg.phantoms.catphan604, "water": pkg.phantoms.water_cylinder,
@@ -34,8 +34,7 @@ def main():
         cfg = pkg.mcio.ScanConfig(n_histories=hist, n_projections=1 if wl == "air" else 894, source_position=pkg.mcio.default_source_position(ph.size_mm))
         inp = pkg.mcio.write_input(cfg, tmp / "x.vox", tmp, tmp / "input.in")
         base = None
-        pools = [x for x in opts.get("pools", "2,3,4").split(",")]
-        tunes = [x for x in opts.get("tunes", "16:12:12:8").split(",")]  # th_w:th_n:th_c:th_r
+        t3 = opts.get("t3", "16").split(",")  # W-batch exit threshold of the wavefront kernel
         configs = []
         for k in kernels:
             if k == 1:
@@ -43,19 +42,16 @@ def main():
             elif k == 2:
                 configs += [(k, t) for t in thresholds]
             else:
-                configs += [(k, f"{pc}/{tu}") for pc in pools for tu in tunes]
+                configs += [(k, t) for t in t3]
         for k, t in configs:
             os.environ["MCGPU_KERNEL"] = str(k)
-            if k == 2:
-                os.environ["MCGPU_W_THRESHOLD"] = t
-            if k == 3:
-                pc, tu = t.split("/")
-                os.environ["MCGPU_POOL"] = pc
-                for name, val in zip(("W", "N", "C", "R"), tu.split(":")):
-                    os.environ[f"MCGPU_POOL_TH_{name}"] = val
+            if k != 1:
+                os.environ["MCGPU_W_THRESHOLD"] = t.split(":")[0]
+                os.environ["MCGPU_WF_ROLES"] = t.split(":")[1] if ":" in t else "0"
+                os.environ["MCGPU_WF_BLOCK"] = t.split(":")[2] if t.count(":") > 1 else "1024"
             eng = pkg.engine.Engine([0])
             eng.load_input(inp).set_voxels(ph.materials, ph.densities, ph.spacing_cm).load_materials()
-            eng.set_fast_math("fast" in opts)
+            eng.set_fast_math(opts.get("fast", "0") != "0")
             info = eng.info
             n = info.num_blocks * info.threads_per_block
             p = 0 if wl == "air" else 100
