@@ -109,9 +109,8 @@ extern "C" int mcgpu_dev_upload(struct mcgpu_device* d, const mcgpu_scene* s, co
     const char* t = getenv("MCGPU_W_THRESHOLD");
     d->kernel_generation = (k && atoi(k) == 1) ? 1 : (k && atoi(k) == 3) ? 3 : 2;
     if (getenv("MCGPU_FAST_MATH")) d->fast_math = atoi(getenv("MCGPU_FAST_MATH")) != 0;  // A/B convenience; the API is mcgpu_set_fast_math
-    d->w_threshold = t ? atoi(t) : (d->kernel_generation == 3 ? 16 : 8);
-    d->wf_roles = getenv("MCGPU_WF_ROLES") ? atoi(getenv("MCGPU_WF_ROLES")) & 31 : 0;
-    d->wf_block = (getenv("MCGPU_WF_BLOCK") && atoi(getenv("MCGPU_WF_BLOCK")) == 512) ? 512 : 1024;
+    d->w_threshold = t ? atoi(t) : (d->kernel_generation == 3 ? 12 : 8);
+    d->wf_block = (getenv("MCGPU_WF_BLOCK") && atoi(getenv("MCGPU_WF_BLOCK")) == 1024) ? 1024 : 512;
     if (d->w_threshold < 1) d->w_threshold = 1;
     if (d->w_threshold > 32) d->w_threshold = 32;
   }

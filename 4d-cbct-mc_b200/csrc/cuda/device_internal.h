@@ -45,7 +45,6 @@ struct mcgpu_device {
   int kernel_generation;                 // 2 = regrouping persistent warps (default), 3 = block wavefront with work queues, 1 = one thread per stream (reference structure, for A/B)
   int w_threshold;
   int wf_block;                          // wavefront kernel: threads per CTA (512: two CTAs per SM, 1024: one)
-  int wf_roles;                          // wavefront kernel: bit s set = warps of SM sub-partition s prefer tracking batches
   int fast_math;                         // 0 = bit-exact arithmetic (default), 1 = the reference's shipped -use_fast_math flags
   uint64_t* h_stage;
   int timed;

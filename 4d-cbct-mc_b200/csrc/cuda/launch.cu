@@ -177,7 +177,7 @@ extern "C" int MCGPU_LAUNCH_NAME(struct mcgpu_device* d, const mcgpu_view* view,
     CK(cudaMemsetAsync(d->d_stream_counter, 0, 2 * sizeof(unsigned long long), d->stream));                                              \
     transport_wavefront<B, DOSE_, ROT_><<<(unsigned)pgrid, wblock, wsmem, d->stream>>>(                                                  \
         d->scene, *view, l->stream_begin, l->stream_end, l->histories_per_thread, l->seed_input, g1, g2, d->d_stream_counter,            \
-        d->w_threshold, pool, pal, d->wf_roles, reinterpret_cast<int*>(d->d_stream_counter + 1));                                        \
+        d->w_threshold, pool, pal, reinterpret_cast<int*>(d->d_stream_counter + 1));                                        \
   }
 #define LAUNCH(B)                                                                                                                        \
   if (d->kernel_generation == 1) {                                                                                                       \

@@ -69,7 +69,7 @@ __device__ __forceinline__ int wf_pack_meta(int state, int scatter_state, int sl
 template <int BITS, bool DOSE, int ROT>
 __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
     transport_wavefront(const SceneDev sc, const __grid_constant__ mcgpu_view vw, long long stream_begin, long long stream_end, int histories_per_thread, int seed_input,
-                        int g1, int g2, unsigned long long* __restrict__ stream_counter, int w_threshold, int pool_size, int palette_entries, int w_roles, int* __restrict__ error_flag) {
+                        int g1, int g2, unsigned long long* __restrict__ stream_counter, int w_threshold, int pool_size, int palette_entries, int* __restrict__ error_flag) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const WfLayout L = wavefront_layout(sc.num_slots, sc.max_shells, palette_entries, pool_size, (int)(blockDim.x >> 5));
   SharedTables& st = *reinterpret_cast<SharedTables*>(smem_raw);
@@ -118,9 +118,6 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
   volatile int* v_avail = ctl->avail;
   volatile int* v_live = &ctl->live;
   volatile int* v_phase = &ctl->phase;
-  const bool sticky = (w_roles & 16) != 0;
-  const bool prefer_w = (w_roles >> ((threadIdx.x >> 5) & 3)) & 1;  // warps of this SM sub-partition prefer tracking batches
-  const bool event_warp = (w_roles & 15) != 0 && !prefer_w;
 
 #define PF(f) pool[(f) * pool_size + pid]
 #define PI(f) pool_i[(f) * pool_size + pid]
@@ -134,7 +131,8 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
       for (;;) {
         const int a0 = v_avail[0], a1 = v_avail[1], a2 = v_avail[2], a3 = v_avail[3];
         int best = -1, a = 0;
-        if (sticky) {  // keep draining the queue the CTA is working on: one kind of code at a time in the SM's instruction cache
+        {  // keep draining the queue the CTA is working on, then move to the fullest one: most warps of
+           // the CTA run the same kind of code, which is what the SM's 32 KB instruction cache rewards
           const int ph = *v_phase;
           const int ap = ph == Q_W ? a0 : ph == Q_N ? a1 : ph == Q_C ? a2 : a3;
           if (ap >= 32) best = ph, a = ap;
@@ -145,19 +143,6 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
             if (a3 > a) best = Q_R, a = a3;
             if (best >= 0 && best != ph) *v_phase = best;
           }
-        } else if (prefer_w && a0 >= 32) best = Q_W, a = a0;  // tracking warps stay in the tracking loop (instruction-cache locality)
-        else if (a2 >= 32) best = Q_C, a = a2;   // full batches first, rarest work first
-        else if (a3 >= 32) best = Q_R, a = a3;
-        else if (a1 >= 32) best = Q_N, a = a1;
-        else if (event_warp && (a1 >= 16 || a2 >= 16)) {  // event warps take half-full event batches before they track
-          if (a2 > a1) best = Q_C, a = a2;
-          else best = Q_N, a = a1;
-        } else if (a0 >= 32) best = Q_W, a = a0;
-        else {                                   // nothing full: the fullest queue
-          if (a0 > a) best = Q_W, a = a0;
-          if (a1 > a) best = Q_N, a = a1;
-          if (a2 > a) best = Q_C, a = a2;
-          if (a3 > a) best = Q_R, a = a3;
         }
         if (best < 0) {
           if (*v_live == 0) break;  // all streams of this CTA are done
@@ -191,6 +176,7 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
       volatile unsigned short* e = rings + q * MCGPU_WF_RING + ((pos + lane) & (MCGPU_WF_RING - 1));
       unsigned v;
       int guard = 0;
+#pragma unroll 1
       while ((v = *e) == MCGPU_WF_EMPTY) {
         if (++guard > (1 << 24)) break;
       }
@@ -401,6 +387,7 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
         if (nq == t) {
           volatile unsigned short* e = rings + t * MCGPU_WF_RING + ((base + __popc(m & lt_mask)) & (MCGPU_WF_RING - 1));
           int guard = 0;
+#pragma unroll 1
           while (*e != MCGPU_WF_EMPTY) {  // its previous occupant is being taken by another warp right now
             if (++guard > (1 << 24)) {
               atomicExch(error_flag, 3);

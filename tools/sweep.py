@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Kernel A/B and tuning sweep on the GPU box: histories/s of one projection for each workload and
-each (MCGPU_KERNEL, MCGPU_W_THRESHOLD) setting (--kernels=1,2,3 --thresholds=8 --t3=12,16,20); every variant is also checked for bit-identical
+each (MCGPU_KERNEL, MCGPU_W_THRESHOLD) setting (--kernels=1,2,3 --thresholds=8 --t3=12:512,12:1024 = W-batch threshold : CTA size); every variant is also checked for bit-identical
 tallies against the first one.  Usage: python tools/sweep.py [workloads...] [--hist N] [--thresholds a,b,c]"""
 import json
 import os
@@ -47,8 +47,7 @@ def main():
             os.environ["MCGPU_KERNEL"] = str(k)
             if k != 1:
                 os.environ["MCGPU_W_THRESHOLD"] = t.split(":")[0]
-                os.environ["MCGPU_WF_ROLES"] = t.split(":")[1] if ":" in t else "0"
-                os.environ["MCGPU_WF_BLOCK"] = t.split(":")[2] if t.count(":") > 1 else "1024"
+                os.environ["MCGPU_WF_BLOCK"] = t.split(":")[1] if ":" in t else "512"
             eng = pkg.engine.Engine([0])
             eng.load_input(inp).set_voxels(ph.materials, ph.densities, ph.spacing_cm).load_materials()
             eng.set_fast_math(opts.get("fast", "0") != "0")
