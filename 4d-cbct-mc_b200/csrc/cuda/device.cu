@@ -107,7 +107,7 @@ extern "C" int mcgpu_dev_upload(struct mcgpu_device* d, const mcgpu_scene* s, co
   {  // tuning / A-B switches (documented in DESIGN.md); the defaults are the product path
     const char* k = getenv("MCGPU_KERNEL");
     const char* t = getenv("MCGPU_W_THRESHOLD");
-    d->kernel_generation = (k && atoi(k) == 1) ? 1 : (k && atoi(k) == 3) ? 3 : 2;
+    d->kernel_generation = (k && atoi(k) == 1) ? 1 : (k && atoi(k) == 2) ? 2 : 3;
     if (getenv("MCGPU_FAST_MATH")) d->fast_math = atoi(getenv("MCGPU_FAST_MATH")) != 0;  // A/B convenience; the API is mcgpu_set_fast_math
     d->w_threshold = t ? atoi(t) : (d->kernel_generation == 3 ? 12 : 8);
     d->wf_block = (getenv("MCGPU_WF_BLOCK") && atoi(getenv("MCGPU_WF_BLOCK")) == 1024) ? 1024 : 512;

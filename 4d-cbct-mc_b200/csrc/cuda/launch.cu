@@ -159,7 +159,7 @@ extern "C" int MCGPU_LAUNCH_NAME(struct mcgpu_device* d, const mcgpu_view* view,
     const size_t fixed = wavefront_layout(d->scene.num_slots, d->scene.max_shells, pal, 0, wblock / 32).total;                           \
     for (; per_sm >= 1; per_sm--) {                                                                                                      \
       const long long budget = (long long)smem_sm / per_sm - 1024 - (long long)fixed;                                                    \
-      pool = budget > 0 ? (int)(budget / (long long)(sizeof(float) * MCGPU_WF_FIELDS)) & ~31 : 0;                                        \
+      pool = budget > 0 ? (int)(budget / (long long)(sizeof(float) * MCGPU_WF_STRIDE)) & ~31 : 0;                                        \
       if (pool > 2 * wblock) pool = 2 * wblock;                                                                                          \
       if (pool > MCGPU_WF_MAX_POOL) pool = MCGPU_WF_MAX_POOL;                                                                            \
       if (pool >= wblock) break;                                                                                                         \

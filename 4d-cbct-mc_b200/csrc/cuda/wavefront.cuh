@@ -31,6 +31,7 @@ namespace MCGPU_NS {
 #define MCGPU_WF_RING 2048  // entries per queue ring; >= pool size, power of two
 #define MCGPU_WF_EMPTY 0xffffu
 #define MCGPU_WF_FIELDS 12
+#define MCGPU_WF_STRIDE 13  // words per context in the pool: odd, so contexts spread over the shared-memory banks
 #define MCGPU_WF_MAX_POOL 2048
 
 enum WfQueue : int { Q_W = 0, Q_N = 1, Q_C = 2, Q_R = 3, Q_COUNT = 4 };
@@ -60,7 +61,7 @@ __host__ __device__ inline WfLayout wavefront_layout(int num_slots, int max_shel
   L.control = (L.palette + sizeof(float2) * palette_entries + 15) & ~size_t(15);
   L.rings = L.control + sizeof(WfControl);
   L.pool = (L.rings + sizeof(unsigned short) * Q_COUNT * MCGPU_WF_RING + 15) & ~size_t(15);
-  L.total = L.pool + sizeof(float) * MCGPU_WF_FIELDS * pool_size;
+  L.total = L.pool + sizeof(float) * MCGPU_WF_STRIDE * pool_size;
   return L;
 }
 
@@ -96,10 +97,10 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
   __syncthreads();
   for (int i = threadIdx.x; i < pool_size; i += blockDim.x) {
     rings[Q_N * MCGPU_WF_RING + i] = (unsigned short)i;
-    pool_i[F_META * pool_size + i] = wf_pack_meta(ST_I, 0, 0);
-    pool_i[F_HIST * pool_size + i] = 0;
-    pool_i[F_S1 * pool_size + i] = 1;
-    pool_i[F_S2 * pool_size + i] = 1;
+    for (int k = 0; k < MCGPU_WF_STRIDE; k++) pool_i[i * MCGPU_WF_STRIDE + k] = 0;
+    pool_i[i * MCGPU_WF_STRIDE + F_META] = wf_pack_meta(ST_I, 0, 0);
+    pool_i[i * MCGPU_WF_STRIDE + F_S1] = 1;
+    pool_i[i * MCGPU_WF_STRIDE + F_S2] = 1;
   }
   if (threadIdx.x == 0) {
     for (int t = 0; t < Q_COUNT; t++) ctl->head[t] = 0u, ctl->tail[t] = 0u, ctl->avail[t] = 0;
@@ -119,8 +120,8 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
   volatile int* v_live = &ctl->live;
   volatile int* v_phase = &ctl->phase;
 
-#define PF(f) pool[(f) * pool_size + pid]
-#define PI(f) pool_i[(f) * pool_size + pid]
+#define PF(f) pool[pid * MCGPU_WF_STRIDE + (f)]
+#define PI(f) pool_i[pid * MCGPU_WF_STRIDE + (f)]
 
   for (;;) {
     // ------------------------------------------------------------------ acquire a batch: up to 32 ids of one queue
@@ -193,13 +194,17 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
 
     Photon p;
     Ranecu rng;
-    int state = ST_F, slot = 0, scatter_state = 0;
+    int state = ST_F, slot = 0, scatter_state = 0, hist_left = 0;
+    float s0 = 0.f;
     p.x = p.y = p.z = p.u = p.v = p.w = p.E = 0.f;
     rng.s1 = rng.s2 = 1;
-    if (act) {
+    if (act) {  // one load / store site for every kind of batch keeps the code small (the kernel is instruction-cache bound)
       const int meta = PI(F_META);
       state = meta & 7, scatter_state = (meta >> 3) & 3, slot = meta >> 8;
       rng.s1 = PI(F_S1), rng.s2 = PI(F_S2);
+      p.x = PF(F_X), p.y = PF(F_Y), p.z = PF(F_Z), p.u = PF(F_U), p.v = PF(F_V), p.w = PF(F_W), p.E = PF(F_E);
+      s0 = PF(F_S0);
+      hist_left = PI(F_HIST);
     }
 
     if (q == Q_W) {
@@ -209,7 +214,6 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
       float mfp_woodcock = 0.f;
       int index = 0, slot_old = -1;
       if (act) {
-        p.x = PF(F_X), p.y = PF(F_Y), p.z = PF(F_Z), p.u = PF(F_U), p.v = PF(F_V), p.w = PF(F_W), p.E = PF(F_E);
         index = __float2int_rd((p.E - sc.e0) * sc.ide);
         const float2 w = __ldg(&sc.woodcock[index]);
         mfp_woodcock = w.x + p.E * w.y;
@@ -250,14 +254,8 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
           }
         }
       } while (__popc(__ballot_sync(MCGPU_FULL_MASK, state == ST_W)) >= thr);
-      if (act) PF(F_X) = p.x, PF(F_Y) = p.y, PF(F_Z) = p.z;
     } else if (q == Q_N) {
       // ---------------------------------------------------------------- T / I / N: tally, next stream, next history
-      int hist_left = 0;
-      if (act) {
-        hist_left = PI(F_HIST);
-        p.x = PF(F_X), p.y = PF(F_Y), p.z = PF(F_Z), p.u = PF(F_U), p.v = PF(F_V), p.w = PF(F_W), p.E = PF(F_E);
-      }
       const int thr = min(16, (n + 1) >> 1);
       for (;;) {
         if (state == ST_T) {  // K:377-381
@@ -292,18 +290,8 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
         }
         if (__popc(__ballot_sync(MCGPU_FULL_MASK, state == ST_T)) < thr) break;
       }
-      if (act) {
-        PF(F_X) = p.x, PF(F_Y) = p.y, PF(F_Z) = p.z, PF(F_U) = p.u, PF(F_V) = p.v, PF(F_W) = p.w, PF(F_E) = p.E;
-        PI(F_HIST) = hist_left;
-      }
     } else {
       // ---------------------------------------------------------------- C / CT / R: one scattering step
-      float s0 = 0.f;
-      if (act) {
-        p.u = PF(F_U), p.v = PF(F_V), p.w = PF(F_W), p.E = PF(F_E);
-        if (DOSE) p.x = PF(F_X), p.y = PF(F_Y), p.z = PF(F_Z);
-        s0 = PF(F_S0);
-      }
       double costh = 0.0;
       bool deflect_pending = false;
       if (q == Q_C) {
@@ -363,14 +351,13 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
           }
         }
       }
-      if (act) {
-        PF(F_U) = p.u, PF(F_V) = p.v, PF(F_W) = p.w, PF(F_E) = p.E;
-        PF(F_S0) = s0;
-      }
     }
 
     // ------------------------------------------------------------------ store what every kind changes, hand the ids on
     if (act) {
+      PF(F_X) = p.x, PF(F_Y) = p.y, PF(F_Z) = p.z, PF(F_U) = p.u, PF(F_V) = p.v, PF(F_W) = p.w, PF(F_E) = p.E;
+      PF(F_S0) = s0;
+      PI(F_HIST) = hist_left;
       PI(F_S1) = rng.s1, PI(F_S2) = rng.s2;
       PI(F_META) = wf_pack_meta(state, scatter_state, slot);
     }

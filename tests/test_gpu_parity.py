@@ -61,23 +61,26 @@ def test_every_voxel_packing_gives_the_same_tallies(pkg, gpu_engine_factory, cas
     eng.close()
 
 
-@pytest.mark.parametrize("generation", ["1", "3"])
+@pytest.mark.parametrize("generation", ["1", "2"])
 @pytest.mark.parametrize("name", ["water_p1", "thorax_oblique", "air"])
 def test_every_kernel_generation_gives_the_same_tallies(pkg, gpu_engine_factory, cases, name, generation, monkeypatch):
-    """The reference-structured kernel (1) and the block-wavefront kernel (3, MCGPU_KERNEL=3) follow the same
-    streams as the default regrouping kernel (2): identical u64 tallies, at two CTA sizes for the wavefront."""
+    """The reference-structured kernel (MCGPU_KERNEL=1) and the regrouping kernel (2) follow the same streams as
+    the default block-wavefront kernel (3): identical u64 tallies, at both CTA sizes of the wavefront kernel."""
     inp, cfg, _ = cases[name]
     eng = gpu_engine_factory(inp)
     p = eng.info.num_projections - 1
     base = eng.run_projection(p)
     eng.close()
     assert base.sum() > 0
-    monkeypatch.setenv("MCGPU_KERNEL", generation)
-    for block in (["512", "1024"] if generation == "3" else ["0"]):
-        monkeypatch.setenv("MCGPU_WF_BLOCK", block)
+    if generation == "2":  # also the other CTA size of the default kernel
+        monkeypatch.setenv("MCGPU_WF_BLOCK", "1024")
         eng = gpu_engine_factory(inp)
-        assert np.array_equal(eng.run_projection(p), base), f"generation {generation} block {block}"
+        assert np.array_equal(eng.run_projection(p), base), "wavefront kernel, 1024-thread CTAs"
         eng.close()
+    monkeypatch.setenv("MCGPU_KERNEL", generation)
+    eng = gpu_engine_factory(inp)
+    assert np.array_equal(eng.run_projection(p), base), f"generation {generation}"
+    eng.close()
 
 
 @pytest.mark.parametrize("name", ["water_p1", "thorax_p4", "air"])
