@@ -295,40 +295,44 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
       double costh = 0.0;
       bool deflect_pending = false;
       if (q == Q_C) {
-        unsigned todo = __ballot_sync(MCGPU_FULL_MASK, act);
+        // The scratch holds 16 photons: lanes [0,16) and [16,32) take turns, two helper lanes per photon.  One
+        // call site serves S0 of the fresh events (pass 0, K:1315-1339) and the S of the trial (pass 1,
+        // K:1359-1402): a single copy of the shell-term code in the instruction stream.
+        const unsigned live = __ballot_sync(MCGPU_FULL_MASK, act);
         const unsigned fresh = __ballot_sync(MCGPU_FULL_MASK, state == ST_C);
-        while (todo) {
-          const unsigned m = limit_rows(todo);  // the scratch holds MCGPU_SCRATCH_ROWS photons
-          todo &= ~m;
-          const bool mine = (m >> lane) & 1u;
-          const unsigned m_c = m & fresh;
-          if (m_c) {  // S0 of fresh events (K:1315-1339)
-            coop_shell_terms(m_c, p.E, slot, 2.f, false, sh_shells, sc, wbuf, stride, lane);
-            if ((m_c >> lane) & 1u) {
-              s0 = compton_ordered_sum<false>(sc.cmp_noscco[slot], wbuf + __popc(m_c & lt_mask) * stride);
-              state = ST_CT;
-            }
-            __syncwarp();
-          }
-          {  // one tau trial per photon (K:1342-1403), rest of GCOa if accepted
-            const ComptonKin kin(p.E);
-            float tau = 1.f;
-            double cdt1 = 0.0;
-            if (mine) cdt1 = compton_propose_tau(kin, p.E, rng, tau);
-            coop_shell_terms(m, p.E, slot, (float)cdt1, true, sh_shells, sc, wbuf, stride, lane);
-            if (mine) {
-              const int nosc = sc.cmp_noscco[slot];
-              float* row = wbuf + __popc(m & lt_mask) * stride;
-              const float s = compton_ordered_sum<true>(nosc, row);
-              if (compton_accept(kin, s0, s, tau, rng)) {
-                const float e_before = p.E;
-                costh = compton_finish(p.E, s, tau, cdt1, sh_shells + slot * MCGPU_MAX_SHELLS, nosc, row, rng);
-                if (DOSE) deposit_energy(sc, p, slot, -1.0f * (p.E - e_before));  // K:296-301, 359
-                deflect_pending = true;
+        const ComptonKin kin(p.E);
+        float tau = 1.f, s = 0.f;
+        double cdt1 = 0.0;
+        if (act) cdt1 = compton_propose_tau(kin, p.E, rng, tau);  // S0 draws no random numbers: the order of the stream is kept
+        const int nosc = sc.cmp_noscco[slot];
+        float* row = wbuf + (lane & 15u) * stride;
+#pragma unroll 1
+        for (int h = 0; h < 2; h++) {
+          const unsigned half = live & (0xffffu << (16 * h));
+          if (!half) continue;
+          const bool mine = (half >> lane) & 1u;
+#pragma unroll 1
+          for (int pass = (half & fresh) ? 0 : 1; pass < 2; pass++) {
+            const unsigned sel = pass == 0 ? (half & fresh) : half;
+            coop_shell_terms_half(h, sel, p.E, slot, pass == 0 ? 2.f : (float)cdt1, pass != 0, sh_shells, sc, wbuf, stride, lane);
+            if ((sel >> lane) & 1u) {
+              const float sum = compton_ordered_sum_rt(nosc, row, pass != 0);
+              if (pass == 0) {
+                s0 = sum;
+                state = ST_CT;
+              } else {
+                s = sum;
               }
             }
             __syncwarp();
           }
+          if (mine && compton_accept(kin, s0, s, tau, rng)) {  // rest of GCOa (K:1405-1513)
+            const float e_before = p.E;
+            costh = compton_finish(p.E, s, tau, cdt1, sh_shells + slot * MCGPU_MAX_SHELLS, nosc, row, rng);
+            if (DOSE) deposit_energy(sc, p, slot, -1.0f * (p.E - e_before));  // K:296-301, 359
+            deflect_pending = true;
+          }
+          __syncwarp();
         }
       } else if (act) {  // Rayleigh (K:329-347); pmax of the bin above, same table entry the tracking step used
         const int index = __float2int_rd((p.E - sc.e0) * sc.ide);
