@@ -367,30 +367,27 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
     }
     __threadfence_block();
     const int nq = !act || state == ST_F ? -1 : state == ST_W ? Q_W : (state == ST_C || state == ST_CT) ? Q_C : state == ST_R ? Q_R : Q_N;
+    {  // lanes bound for the same queue find each other with one match: one reservation per queue, no loop over queues
+      const unsigned peers = __match_any_sync(MCGPU_FULL_MASK, nq);
+      const int leader = __ffs(peers) - 1, cnt = __popc(peers);
+      unsigned base = 0;
+      if (nq >= 0 && (int)lane == leader) base = atomicAdd(&ctl->tail[nq], (unsigned)cnt);
+      base = __shfl_sync(MCGPU_FULL_MASK, base, leader);
+      if (nq >= 0) {
+        volatile unsigned short* e = rings + nq * MCGPU_WF_RING + ((base + __popc(peers & lt_mask)) & (MCGPU_WF_RING - 1));
+        int guard = 0;
 #pragma unroll 1
-    for (int t = 0; t < Q_COUNT; t++) {
-      const unsigned m = __ballot_sync(MCGPU_FULL_MASK, nq == t);
-      if (m) {
-        const int leader = __ffs(m) - 1;
-        unsigned base = 0;
-        if ((int)lane == leader) base = atomicAdd(&ctl->tail[t], (unsigned)__popc(m));
-        base = __shfl_sync(MCGPU_FULL_MASK, base, leader);
-        if (nq == t) {
-          volatile unsigned short* e = rings + t * MCGPU_WF_RING + ((base + __popc(m & lt_mask)) & (MCGPU_WF_RING - 1));
-          int guard = 0;
-#pragma unroll 1
-          while (*e != MCGPU_WF_EMPTY) {  // its previous occupant is being taken by another warp right now
-            if (++guard > (1 << 24)) {
-              atomicExch(error_flag, 3);
-              break;
-            }
+        while (*e != MCGPU_WF_EMPTY) {  // its previous occupant is being taken by another warp right now
+          if (++guard > (1 << 24)) {
+            atomicExch(error_flag, 3);
+            break;
           }
-          *e = (unsigned short)pid;
         }
-        __threadfence_block();
-        __syncwarp();
-        if ((int)lane == leader) atomicAdd(&ctl->avail[t], __popc(m));
+        *e = (unsigned short)pid;
       }
+      __threadfence_block();
+      __syncwarp();
+      if (nq >= 0 && (int)lane == leader) atomicAdd(&ctl->avail[nq], cnt);
     }
     {
       const unsigned m_f = __ballot_sync(MCGPU_FULL_MASK, act && state == ST_F);
