@@ -110,6 +110,8 @@ extern "C" int mcgpu_dev_upload(struct mcgpu_device* d, const mcgpu_scene* s, co
     d->kernel_generation = (k && atoi(k) == 1) ? 1 : (k && atoi(k) == 2) ? 2 : 3;
     if (getenv("MCGPU_FAST_MATH")) d->fast_math = atoi(getenv("MCGPU_FAST_MATH")) != 0;  // A/B convenience; the API is mcgpu_set_fast_math
     d->w_threshold = t ? atoi(t) : (d->kernel_generation == 3 ? 12 : 8);
+    d->wf_rows = getenv("MCGPU_WF_ROWS") ? atoi(getenv("MCGPU_WF_ROWS")) : 0;
+    if (d->wf_rows != 16 && d->wf_rows != 32) d->wf_rows = 0;
     d->wf_block = (getenv("MCGPU_WF_BLOCK") && atoi(getenv("MCGPU_WF_BLOCK")) == 1024) ? 1024 : 512;
     if (d->w_threshold < 1) d->w_threshold = 1;
     if (d->w_threshold > 32) d->w_threshold = 32;

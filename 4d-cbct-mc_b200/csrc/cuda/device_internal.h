@@ -44,6 +44,7 @@ struct mcgpu_device {
   unsigned long long* d_stream_counter;  // [0] next stream of the running launch (persistent kernels), [1] kernel error flag (wavefront)
   int kernel_generation;                 // 3 = block wavefront with work queues (default), 2 = regrouping persistent warps, 1 = one thread per stream (reference structure); 1 and 2 for A/B
   int w_threshold;
+  int wf_rows;                           // wavefront kernel: scratch rows per warp (16, 32; 0 = choose by shared-memory budget)
   int wf_block;                          // wavefront kernel: threads per CTA (512: two CTAs per SM, 1024: one)
   int fast_math;                         // 0 = bit-exact arithmetic (default), 1 = the reference's shipped -use_fast_math flags
   uint64_t* h_stage;

@@ -156,7 +156,12 @@ extern "C" int MCGPU_LAUNCH_NAME(struct mcgpu_device* d, const mcgpu_view* view,
     const int wblock = d->wf_block;                                                                                                      \
     int smem_sm = 0, per_sm = MCGPU_WF_MAX_BLOCK / wblock, pool = 0;                                                                     \
     CK(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, d->ordinal));                                       \
-    const size_t fixed = wavefront_layout(d->scene.num_slots, d->scene.max_shells, pal, 0, wblock / 32).total;                           \
+    int rows = d->wf_rows;                                                                                                               \
+    if (rows == 0) { /* 32 scratch rows when the full pool still fits next to them */                                                       \
+      const long long b32 = (long long)smem_sm / per_sm - 1024 - (long long)wavefront_layout(d->scene.num_slots, d->scene.max_shells, pal, 0, wblock / 32, 32).total; \
+      rows = b32 >= (long long)(sizeof(float) * MCGPU_WF_STRIDE) * (2 * wblock) ? 32 : 16;                                               \
+    }                                                                                                                                    \
+    const size_t fixed = wavefront_layout(d->scene.num_slots, d->scene.max_shells, pal, 0, wblock / 32, rows).total;                     \
     for (; per_sm >= 1; per_sm--) {                                                                                                      \
       const long long budget = (long long)smem_sm / per_sm - 1024 - (long long)fixed;                                                    \
       pool = budget > 0 ? (int)(budget / (long long)(sizeof(float) * MCGPU_WF_STRIDE)) & ~31 : 0;                                        \
@@ -168,7 +173,7 @@ extern "C" int MCGPU_LAUNCH_NAME(struct mcgpu_device* d, const mcgpu_view* view,
       snprintf(err, errlen, "device %d: not enough shared memory for the wavefront kernel", d->ordinal);                                 \
       return -1;                                                                                                                         \
     }                                                                                                                                    \
-    const size_t wsmem = wavefront_layout(d->scene.num_slots, d->scene.max_shells, pal, pool, wblock / 32).total;                        \
+    const size_t wsmem = wavefront_layout(d->scene.num_slots, d->scene.max_shells, pal, pool, wblock / 32, rows).total;                        \
     CK(cudaFuncSetAttribute(transport_wavefront<B, DOSE_, ROT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));              \
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, transport_wavefront<B, DOSE_, ROT_>, wblock, wsmem));                      \
     long long pgrid = (long long)d->sm_count * (per_sm > 0 ? per_sm : 1);                                                                \
@@ -177,7 +182,7 @@ extern "C" int MCGPU_LAUNCH_NAME(struct mcgpu_device* d, const mcgpu_view* view,
     CK(cudaMemsetAsync(d->d_stream_counter, 0, 2 * sizeof(unsigned long long), d->stream));                                              \
     transport_wavefront<B, DOSE_, ROT_><<<(unsigned)pgrid, wblock, wsmem, d->stream>>>(                                                  \
         d->scene, *view, l->stream_begin, l->stream_end, l->histories_per_thread, l->seed_input, g1, g2, d->d_stream_counter,            \
-        d->w_threshold, pool, pal, reinterpret_cast<int*>(d->d_stream_counter + 1));                                        \
+        d->w_threshold, pool, pal, rows, reinterpret_cast<int*>(d->d_stream_counter + 1));                                        \
   }
 #define LAUNCH(B)                                                                                                                        \
   if (d->kernel_generation == 1) {                                                                                                       \

@@ -28,7 +28,6 @@
 namespace MCGPU_NS {
 
 #define MCGPU_WF_MAX_BLOCK 1024
-#define MCGPU_WF_RING 2048  // entries per queue ring; >= pool size, power of two
 #define MCGPU_WF_EMPTY 0xffffu
 #define MCGPU_WF_FIELDS 12
 #define MCGPU_WF_STRIDE 13  // words per context in the pool: odd, so contexts spread over the shared-memory banks
@@ -50,17 +49,20 @@ struct WfControl {
 // shared-memory carve-up, used by the kernel and by the host to size the launch
 struct WfLayout {
   size_t shells, scratch, palette, control, rings, pool, total;
-  int stride;
+  int stride, ring;
 };
-__host__ __device__ inline WfLayout wavefront_layout(int num_slots, int max_shells, int palette_entries, int pool_size, int warps) {
+// `rows` = photons per cooperative Compton pass (16 or 32 scratch rows per warp); the rings hold 64 ids per warp
+// (>= the pool, which is at most 2 contexts per thread; a power of two)
+__host__ __device__ inline WfLayout wavefront_layout(int num_slots, int max_shells, int palette_entries, int pool_size, int warps, int rows) {
   WfLayout L;
   L.stride = regroup_scratch_stride(max_shells);
+  L.ring = warps <= 16 ? 1024 : 2048;
   L.shells = (sizeof(SharedTables) + 15) & ~size_t(15);
   L.scratch = L.shells + sizeof(float4) * num_slots * MCGPU_MAX_SHELLS;
-  L.palette = (L.scratch + sizeof(float) * warps * MCGPU_SCRATCH_ROWS * L.stride + 15) & ~size_t(15);
+  L.palette = (L.scratch + sizeof(float) * warps * rows * L.stride + 15) & ~size_t(15);
   L.control = (L.palette + sizeof(float2) * palette_entries + 15) & ~size_t(15);
   L.rings = L.control + sizeof(WfControl);
-  L.pool = (L.rings + sizeof(unsigned short) * Q_COUNT * MCGPU_WF_RING + 15) & ~size_t(15);
+  L.pool = (L.rings + sizeof(unsigned short) * Q_COUNT * L.ring + 15) & ~size_t(15);
   L.total = L.pool + sizeof(float) * MCGPU_WF_STRIDE * pool_size;
   return L;
 }
@@ -70,9 +72,10 @@ __device__ __forceinline__ int wf_pack_meta(int state, int scatter_state, int sl
 template <int BITS, bool DOSE, int ROT>
 __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
     transport_wavefront(const SceneDev sc, const __grid_constant__ mcgpu_view vw, long long stream_begin, long long stream_end, int histories_per_thread, int seed_input,
-                        int g1, int g2, unsigned long long* __restrict__ stream_counter, int w_threshold, int pool_size, int palette_entries, int* __restrict__ error_flag) {
+                        int g1, int g2, unsigned long long* __restrict__ stream_counter, int w_threshold, int pool_size, int palette_entries, int rows, int* __restrict__ error_flag) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const WfLayout L = wavefront_layout(sc.num_slots, sc.max_shells, palette_entries, pool_size, (int)(blockDim.x >> 5));
+  const WfLayout L = wavefront_layout(sc.num_slots, sc.max_shells, palette_entries, pool_size, (int)(blockDim.x >> 5), rows);
+  const int ring = L.ring, ring_mask = L.ring - 1;
   SharedTables& st = *reinterpret_cast<SharedTables*>(smem_raw);
   float4* sh_shells = reinterpret_cast<float4*>(smem_raw + L.shells);
   float* sh_scratch = reinterpret_cast<float*>(smem_raw + L.scratch);
@@ -93,10 +96,10 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
   if (BITS == 4 || BITS == 8)
     for (int i = threadIdx.x; i < sc.palette_size; i += blockDim.x) sh_palette[i] = sc.palette[i];
   // every context starts in Q_N asking for a stream
-  for (int i = threadIdx.x; i < Q_COUNT * MCGPU_WF_RING; i += blockDim.x) rings[i] = MCGPU_WF_EMPTY;
+  for (int i = threadIdx.x; i < Q_COUNT * ring; i += blockDim.x) rings[i] = MCGPU_WF_EMPTY;
   __syncthreads();
   for (int i = threadIdx.x; i < pool_size; i += blockDim.x) {
-    rings[Q_N * MCGPU_WF_RING + i] = (unsigned short)i;
+    rings[Q_N * ring + i] = (unsigned short)i;
     for (int k = 0; k < MCGPU_WF_STRIDE; k++) pool_i[i * MCGPU_WF_STRIDE + k] = 0;
     pool_i[i * MCGPU_WF_STRIDE + F_META] = wf_pack_meta(ST_I, 0, 0);
     pool_i[i * MCGPU_WF_STRIDE + F_S1] = 1;
@@ -114,7 +117,7 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
 
   const unsigned lane = threadIdx.x & 31u;
   const unsigned lt_mask = (1u << lane) - 1u;
-  float* wbuf = sh_scratch + (threadIdx.x >> 5) * MCGPU_SCRATCH_ROWS * stride;
+  float* wbuf = sh_scratch + (threadIdx.x >> 5) * rows * stride;
   const long long n_streams = stream_end - stream_begin;
   volatile int* v_avail = ctl->avail;
   volatile int* v_live = &ctl->live;
@@ -174,7 +177,7 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
     bool act = (int)lane < n;
     int pid = 0;
     if (act) {
-      volatile unsigned short* e = rings + q * MCGPU_WF_RING + ((pos + lane) & (MCGPU_WF_RING - 1));
+      volatile unsigned short* e = rings + q * ring + ((pos + lane) & ring_mask);
       unsigned v;
       int guard = 0;
 #pragma unroll 1
@@ -295,7 +298,8 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
       double costh = 0.0;
       bool deflect_pending = false;
       if (q == Q_C) {
-        // The scratch holds 16 photons: lanes [0,16) and [16,32) take turns, two helper lanes per photon.  One
+        // The scratch holds `rows` photons (16: lanes [0,16) and [16,32) take turns, two helper lanes per photon;
+        // 32 when the scene's shell count leaves room: one turn, each lane evaluates its own photon).  One
         // call site serves S0 of the fresh events (pass 0, K:1315-1339) and the S of the trial (pass 1,
         // K:1359-1402): a single copy of the shell-term code in the instruction stream.
         const unsigned live = __ballot_sync(MCGPU_FULL_MASK, act);
@@ -305,16 +309,16 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
         double cdt1 = 0.0;
         if (act) cdt1 = compton_propose_tau(kin, p.E, rng, tau);  // S0 draws no random numbers: the order of the stream is kept
         const int nosc = sc.cmp_noscco[slot];
-        float* row = wbuf + (lane & 15u) * stride;
+        float* row = wbuf + (lane & (unsigned)(rows - 1)) * stride;
 #pragma unroll 1
-        for (int h = 0; h < 2; h++) {
-          const unsigned half = live & (0xffffu << (16 * h));
+        for (int h = 0; h < (rows == 32 ? 1 : 2); h++) {
+          const unsigned half = rows == 32 ? live : live & (0xffffu << (16 * h));
           if (!half) continue;
           const bool mine = (half >> lane) & 1u;
 #pragma unroll 1
           for (int pass = (half & fresh) ? 0 : 1; pass < 2; pass++) {
             const unsigned sel = pass == 0 ? (half & fresh) : half;
-            coop_shell_terms_half(h, sel, p.E, slot, pass == 0 ? 2.f : (float)cdt1, pass != 0, sh_shells, sc, wbuf, stride, lane);
+            coop_shell_terms_half(h, rows, sel, p.E, slot, pass == 0 ? 2.f : (float)cdt1, pass != 0, sh_shells, sc, wbuf, stride, lane);
             if ((sel >> lane) & 1u) {
               const float sum = compton_ordered_sum_rt(nosc, row, pass != 0);
               if (pass == 0) {
@@ -374,7 +378,7 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
       if (nq >= 0 && (int)lane == leader) base = atomicAdd(&ctl->tail[nq], (unsigned)cnt);
       base = __shfl_sync(MCGPU_FULL_MASK, base, leader);
       if (nq >= 0) {
-        volatile unsigned short* e = rings + nq * MCGPU_WF_RING + ((base + __popc(peers & lt_mask)) & (MCGPU_WF_RING - 1));
+        volatile unsigned short* e = rings + nq * ring + ((base + __popc(peers & lt_mask)) & ring_mask);
         int guard = 0;
 #pragma unroll 1
         while (*e != MCGPU_WF_EMPTY) {  // its previous occupant is being taken by another warp right now

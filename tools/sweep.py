@@ -48,6 +48,7 @@ def main():
             if k != 1:
                 os.environ["MCGPU_W_THRESHOLD"] = t.split(":")[0]
                 os.environ["MCGPU_WF_BLOCK"] = t.split(":")[1] if ":" in t else "512"
+                os.environ["MCGPU_WF_ROWS"] = t.split(":")[2] if t.count(":") > 1 else "0"
             eng = pkg.engine.Engine([0])
             eng.load_input(inp).set_voxels(ph.materials, ph.densities, ph.spacing_cm).load_materials()
             eng.set_fast_math(opts.get("fast", "0") != "0")
