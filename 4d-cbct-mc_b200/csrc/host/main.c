@@ -8,7 +8,12 @@
  *     scrapes for its progress bar, and never the substring "error" on success (Q9);
  *   - it tolerates being started N times by `mpirun -n N`: there is no MPI in this engine, one
  *     process drives every visible GPU, so ranks other than 0 (as seen in the launcher's
- *     environment) exit 0 immediately. */
+ *     environment) exit 0 immediately.
+ *
+ * Built with -DMCGPU_BATCH_MAIN the same file gives MC-GPU_v1.3_batch.x <a.in> <b.in> ...: the 4D case
+ * (one input file per respiratory phase, cbctmc/mc/simulation.py:622-692) in ONE process, so that the CUDA
+ * context and the device buffers are set up once instead of once per phase.  Every input
+ * is simulated exactly as a separate invocation would (same seeds, same files). */
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -42,17 +47,63 @@ static int die(mcgpu_ctx* ctx, int rc) {
   return rc;
 }
 
-int main(int argc, char** argv) {
-  struct timespec t0, t1, t2;
-  mcgpu_ctx* ctx;
+static int run_one(mcgpu_ctx* ctx, const char* in_path, const struct timespec* t0) {
+  struct timespec t1, t2;
   mcgpu_info info;
-  time_t now = time(NULL);
   double t_init, t_total;
   int rc;
+  printf("\n    -- Reading the input file '%s':\n", in_path);
+  if ((rc = mcgpu_load_input(ctx, in_path)) != MCGPU_OK) return rc;
+  if ((rc = mcgpu_load_voxels(ctx, NULL)) != MCGPU_OK) return rc;
+  if ((rc = mcgpu_load_materials(ctx, NULL, 0)) != MCGPU_OK) return rc;
+  mcgpu_get_info(ctx, &info);
+  printf("              x-ray tracks to simulate = %llu\n", info.requested_histories);
+  printf("                   initial random seed = %d\n", info.seed_input);
+  printf("                number of pixels image = %dx%d = %d\n", info.num_pixels_x, info.num_pixels_z, info.num_pixels_x * info.num_pixels_z);
+  printf("                 number of projections = %d\n", info.num_projections);
+  printf("            number of energy bins read = %d\n", info.num_spectrum_bins);
+  printf("                  mean energy spectrum = %.3f keV\n", 0.001f * info.mean_energy_spectrum);
+  printf("       Number of voxels in the input geometry file: %d x %d x %d\n", info.num_voxels_x, info.num_voxels_y, info.num_voxels_z);
+  printf("       Packed voxel layout: %d bits per voxel, %d distinct (material, density) pairs, %d materials in use\n", info.voxel_bits, info.palette_size, info.num_materials_used);
+  printf("       Number of energy values in the mean free path database: %d\n", info.num_energy_values);
+  printf("       ==> CUDA: %d device(s) in use; executing %d blocks of %d threads, %d histories per thread: %llu histories per projection\n", info.num_devices, info.num_blocks,
+         info.threads_per_block, info.histories_per_thread, info.launched_histories);
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  t_init = (t1.tv_sec - t0->tv_sec) + 1e-9 * (t1.tv_nsec - t0->tv_nsec);
+  printf("\n    -- INITIALIZATION finished: elapsed time = %.3f s. \n\n", t_init);
+  printf("\n\n    -- MONTE CARLO LOOP phase.\n\n");
+  fflush(stdout);
+
+  if (info.num_devices < 1) return MCGPU_E_CUDA;
+  if ((rc = mcgpu_run_all(ctx, on_projection, NULL)) != MCGPU_OK) return rc;
+
+  clock_gettime(CLOCK_MONOTONIC, &t2);
+  t_total = (t2.tv_sec - t0->tv_sec) + 1e-9 * (t2.tv_nsec - t0->tv_nsec);
+  mcgpu_get_info(ctx, &info);
+  printf("\n\n\n    -- SIMULATION FINISHED!\n");
+  printf("\n\n       ****** TOTAL SIMULATION PERFORMANCE (including initialization and reporting) ******\n\n");
+  printf("          >>> Execution time including initialization, transport and report: %.3f s.\n", t_total);
+  printf("          >>> Time spent in the Monte Carlo transport and reporting: %.3f s.\n", t_total - t_init);
+  printf("          >>> Total number of simulated x rays:  %llu\n", info.launched_histories * (unsigned long long)info.num_projections);
+  if (t_total > 0.000001)
+    printf("          >>> Total speed (including initialization time) [x-rays/s]:  %.2f\n\n", (double)(info.launched_histories * (unsigned long long)info.num_projections) / t_total);
+  fflush(stdout);
+  return MCGPU_OK;
+}
+
+int main(int argc, char** argv) {
+  struct timespec t0;
+  mcgpu_ctx* ctx;
+  time_t now = time(NULL);
+  int rc, k;
 
   if (launcher_rank() != 0) return 0;
   clock_gettime(CLOCK_MONOTONIC, &t0);
+#ifdef MCGPU_BATCH_MAIN
+  if (argc < 2) {
+#else
   if (argc != 2) {
+#endif
     printf("\n\n   !!read_input!! %s\n\n", argc > 2 ? "Too many input parameters: provide only the input file name." : "Input file name not given as an execution parameter.");
     return -1;
   }
@@ -71,41 +122,10 @@ int main(int argc, char** argv) {
     return -4;
   }
   mcgpu_set_verbose(ctx, 1);
-  printf("\n    -- Reading the input file '%s':\n", argv[1]);
-  if ((rc = mcgpu_load_input(ctx, argv[1])) != MCGPU_OK) return die(ctx, rc);
-  if ((rc = mcgpu_load_voxels(ctx, NULL)) != MCGPU_OK) return die(ctx, rc);
-  if ((rc = mcgpu_load_materials(ctx, NULL, 0)) != MCGPU_OK) return die(ctx, rc);
-  mcgpu_get_info(ctx, &info);
-  printf("              x-ray tracks to simulate = %llu\n", info.requested_histories);
-  printf("                   initial random seed = %d\n", info.seed_input);
-  printf("                number of pixels image = %dx%d = %d\n", info.num_pixels_x, info.num_pixels_z, info.num_pixels_x * info.num_pixels_z);
-  printf("                 number of projections = %d\n", info.num_projections);
-  printf("            number of energy bins read = %d\n", info.num_spectrum_bins);
-  printf("                  mean energy spectrum = %.3f keV\n", 0.001f * info.mean_energy_spectrum);
-  printf("       Number of voxels in the input geometry file: %d x %d x %d\n", info.num_voxels_x, info.num_voxels_y, info.num_voxels_z);
-  printf("       Packed voxel layout: %d bits per voxel, %d distinct (material, density) pairs, %d materials in use\n", info.voxel_bits, info.palette_size, info.num_materials_used);
-  printf("       Number of energy values in the mean free path database: %d\n", info.num_energy_values);
-  printf("       ==> CUDA: %d device(s) in use; executing %d blocks of %d threads, %d histories per thread: %llu histories per projection\n", info.num_devices, info.num_blocks,
-         info.threads_per_block, info.histories_per_thread, info.launched_histories);
-  clock_gettime(CLOCK_MONOTONIC, &t1);
-  t_init = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
-  printf("\n    -- INITIALIZATION finished: elapsed time = %.3f s. \n\n", t_init);
-  printf("\n\n    -- MONTE CARLO LOOP phase.\n\n");
-  fflush(stdout);
-
-  if (info.num_devices < 1) return die(ctx, MCGPU_E_CUDA);
-  if ((rc = mcgpu_run_all(ctx, on_projection, NULL)) != MCGPU_OK) return die(ctx, rc);
-
-  clock_gettime(CLOCK_MONOTONIC, &t2);
-  t_total = (t2.tv_sec - t0.tv_sec) + 1e-9 * (t2.tv_nsec - t0.tv_nsec);
-  mcgpu_get_info(ctx, &info);
-  printf("\n\n\n    -- SIMULATION FINISHED!\n");
-  printf("\n\n       ****** TOTAL SIMULATION PERFORMANCE (including initialization and reporting) ******\n\n");
-  printf("          >>> Execution time including initialization, transport and report: %.3f s.\n", t_total);
-  printf("          >>> Time spent in the Monte Carlo transport and reporting: %.3f s.\n", t_total - t_init);
-  printf("          >>> Total number of simulated x rays:  %llu\n", info.launched_histories * (unsigned long long)info.num_projections);
-  if (t_total > 0.000001)
-    printf("          >>> Total speed (including initialization time) [x-rays/s]:  %.2f\n\n", (double)(info.launched_histories * (unsigned long long)info.num_projections) / t_total);
+  for (k = 1; k < argc; k++) {
+    if (k > 1) clock_gettime(CLOCK_MONOTONIC, &t0);
+    if ((rc = run_one(ctx, argv[k], &t0)) != MCGPU_OK) return die(ctx, rc);
+  }
   now = time(NULL);
   printf("\n****** Code execution finished on: %s\n\n", ctime(&now));
   mcgpu_destroy(ctx);

@@ -24,7 +24,7 @@ CUDA_HDR := $(CUDADIR)/transport.cuh $(CUDADIR)/regroup.cuh $(CUDADIR)/wavefront
 all: lib exe oracle
 
 lib: $(LIBDIR)/libmcgpu_b200.so
-exe: $(BINDIR)/MC-GPU_v1.3.x
+exe: $(BINDIR)/MC-GPU_v1.3.x $(BINDIR)/MC-GPU_v1.3_batch.x
 oracle:
 	$(MAKE) -C oracle
 
@@ -54,6 +54,11 @@ $(LIBDIR)/libmcgpu_b200.so: $(HOST_OBJ) $(CUDA_OBJ)
 $(BINDIR)/MC-GPU_v1.3.x: $(HOSTDIR)/main.c $(LIBDIR)/libmcgpu_b200.so
 	@mkdir -p $(BINDIR)
 	$(CC) $(CFLAGS) -fPIE $< -o $@ -L$(LIBDIR) -lmcgpu_b200 -Wl,-rpath,'$$ORIGIN/../lib'
+
+# several input files (the respiratory phases of a 4D scan) in one process: one CUDA context
+$(BINDIR)/MC-GPU_v1.3_batch.x: $(HOSTDIR)/main.c $(LIBDIR)/libmcgpu_b200.so
+	@mkdir -p $(BINDIR)
+	$(CC) $(CFLAGS) -DMCGPU_BATCH_MAIN -fPIE $< -o $@ -L$(LIBDIR) -lmcgpu_b200 -Wl,-rpath,'$$ORIGIN/../lib'
 
 clean:
 	rm -rf $(BUILD) $(LIBDIR) $(BINDIR)

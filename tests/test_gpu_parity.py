@@ -177,6 +177,23 @@ def test_executable_is_a_drop_in(pkg, gpu_engine_factory, tmp_path):
     eng.close()
 
 
+def test_batch_executable_serves_several_inputs_in_one_process(pkg, gpu_engine_factory, tmp_path):
+    """4D batching: MC-GPU_v1.3_batch.x a.in b.in ... = the separate invocations, one CUDA context."""
+    inputs = [build_case(pkg, name, tmp_path / name) for name in ("water_p1", "catphan_angles", "thorax_oblique")]
+    exe = ROOT / "4d-cbct-mc_b200" / "bin" / "MC-GPU_v1.3_batch.x"
+    res = subprocess.run([str(exe)] + [str(i[0]) for i in inputs], capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-2000:]
+    assert not re.search(r"(?i)error", res.stdout)
+    assert len(re.findall(r"SIMULATION FINISHED", res.stdout)) == 3
+    for inp, cfg, _ in inputs:
+        eng = gpu_engine_factory(inp)
+        last_writer = {Path(eng.projection_filename(p)): p for p in range(eng.info.num_projections)}
+        for f, p in last_writer.items():
+            cnt = pkg.mcio.projection_counts(pkg.mcio.read_projection(f, cfg.n_detector_pixels), cfg.n_detector_pixels, det_cm(cfg), eng.info.launched_histories)
+            assert np.array_equal(cnt, eng.run_projection(p)), (inp, p)
+        eng.close()
+
+
 def test_full_size_properties(pkg, gpu_engine_factory, tmp_path):
     """BASELINE.json sizes: 256x256x100 thorax at 2 mm, 1848x768 detector, default half-fan geometry."""
     ph = pkg.phantoms.thorax()

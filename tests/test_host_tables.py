@@ -154,3 +154,22 @@ def test_product_host_matches_the_reference_own_host_code(pkg, oracle_py, cases,
             b = np.frombuffer(cmp_[k * 4000:(k + 1) * 4000], dtype=np.float32).reshape(40, 25)
             for m in used:
                 assert np.array_equal(bits(a[:nos[m], m]), bits(b[:nos[m], m])), (t, m)
+
+
+def test_one_context_serves_several_inputs_in_turn(pkg, cases):
+    """4D batching: a context is re-loaded with the next phase's input; nothing of the previous one leaks."""
+    fresh = {}
+    for name in ("water_p1", "thorax_p4"):
+        with pkg.engine.Engine() as eng:
+            eng.load_input(cases[name][0]).load_voxels().load_materials()
+            fresh[name] = (eng.info, eng.table("views"), eng.table("mfp_a"), eng.table("voxel_packed"))
+    with pkg.engine.Engine() as eng:
+        for name in ("water_p1", "thorax_p4", "water_p1"):
+            eng.load_input(cases[name][0]).load_voxels().load_materials()
+            info, views, mfp, packed = fresh[name]
+            now = eng.info
+            assert (now.num_projections, now.launched_histories, now.voxel_bits, now.palette_size, now.num_materials_used) == (
+                info.num_projections, info.launched_histories, info.voxel_bits, info.palette_size, info.num_materials_used)
+            assert np.array_equal(eng.table("views"), views)
+            assert np.array_equal(eng.table("mfp_a"), mfp)
+            assert np.array_equal(eng.table("voxel_packed"), packed)
