@@ -4,9 +4,9 @@ The directory name is the one the build contract fixes; it is not a valid Python
 identifier, so load it with `__graft_entry__.import_package()` which registers
 it as the module `cbctmc_b200`.
 """
-from . import mcio, phantoms, sharding  # noqa: F401
+from . import mcio, phantoms, postprocess, sharding  # noqa: F401
 
-__all__ = ["mcio", "phantoms", "sharding", "engine"]
+__all__ = ["mcio", "phantoms", "postprocess", "sharding", "engine"]
 
 
 def __getattr__(name):

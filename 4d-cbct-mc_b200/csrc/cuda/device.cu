@@ -58,6 +58,8 @@ static void free_scene_allocs(mcgpu_device* d) {
 extern "C" void mcgpu_dev_close(struct mcgpu_device* d) {
   if (!d) return;
   cudaSetDevice(d->ordinal);
+  cudaFree(d->post_ws);
+  d->post_ws = NULL, d->post_ws_bytes = 0;
   cudaStreamSynchronize(d->stream);
   free_scene_allocs(d);
   cudaEventDestroy(d->ev0), cudaEventDestroy(d->ev1);

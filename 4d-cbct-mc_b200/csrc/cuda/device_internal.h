@@ -48,6 +48,8 @@ struct mcgpu_device {
   int wf_block;                          // wavefront kernel: threads per CTA (512: two CTAs per SM, 1024: one)
   int fast_math;                         // 0 = bit-exact arithmetic (default), 1 = the reference's shipped -use_fast_math flags
   uint64_t* h_stage;
+  void* post_ws;                         // workspace of the post-processing kernels (postprocess.cu)
+  size_t post_ws_bytes;
   int timed;
 };
 

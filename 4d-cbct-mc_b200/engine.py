@@ -54,6 +54,9 @@ _SIGS = {
     "mcgpu_run_all": (C.c_int, [C.c_void_p, PROGRESS_CB, C.c_void_p]),
     "mcgpu_write_projection_ascii": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_double]),
     "mcgpu_write_projection_raw": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "mcgpu_post_intensity": (C.c_int, [C.c_void_p, C.c_void_p, C.c_ulonglong, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mcgpu_post_gaussian": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p]),
+    "mcgpu_post_normalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_float]),
     "mcgpu_projection_filename": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_size_t]),
     "mcgpu_reset_dose": (C.c_int, [C.c_void_p]),
     "mcgpu_get_dose": (C.c_longlong, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t]),
@@ -218,6 +221,31 @@ class Engine:
     def write_projection_raw(self, p: int, image: np.ndarray):
         img = np.ascontiguousarray(image, dtype=np.uint64)
         self._check(_lib.mcgpu_write_projection_raw(self._h, p, img.ctypes.data))
+
+    # ---- projection post-processing on the device (include/mcgpu_b200.h)
+    def post_intensity(self, tally: np.ndarray | None = None, launched: int | None = None, crop_x: int = 0):
+        """(total, unscattered, scattered, min_positive[3]) float32 [Nz][crop_x]; tally None = the device's last projection."""
+        info = self.info
+        crop = crop_x if 0 < crop_x <= info.num_pixels_x else info.num_pixels_x
+        outs = [np.empty((info.num_pixels_z, crop), dtype=np.float32) for _ in range(3)]
+        mins = np.empty(3, dtype=np.float32)
+        t = None if tally is None else np.ascontiguousarray(tally, dtype=np.uint64)
+        self._check(_lib.mcgpu_post_intensity(self._h, None if t is None else t.ctypes.data, int(launched or info.launched_histories), crop,
+                                              outs[0].ctypes.data, outs[1].ctypes.data, outs[2].ctypes.data, mins.ctypes.data))
+        return outs[0], outs[1], outs[2], mins
+
+    def post_gaussian(self, image: np.ndarray, sigma) -> np.ndarray:
+        a = np.ascontiguousarray(image, dtype=np.float32)
+        out = np.empty_like(a)
+        self._check(_lib.mcgpu_post_gaussian(self._h, a.ctypes.data, a.shape[0], a.shape[1], float(sigma[0]), float(sigma[1]), out.ctypes.data))
+        return out
+
+    def post_normalize(self, air: np.ndarray, stack: np.ndarray, min_nonzero: float) -> np.ndarray:
+        """In place on a C-contiguous float32 stack [P][Nz][Nx]."""
+        a = np.ascontiguousarray(air, dtype=np.float32)
+        assert stack.dtype == np.float32 and stack.flags.c_contiguous and stack.shape[1:] == a.shape
+        self._check(_lib.mcgpu_post_normalize(self._h, a.ctypes.data, stack.ctypes.data, stack.shape[0], a.shape[0], a.shape[1], float(min_nonzero)))
+        return stack
 
     def reset_dose(self):
         self._check(_lib.mcgpu_reset_dose(self._h))

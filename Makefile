@@ -16,9 +16,9 @@ CFLAGS   := -std=gnu11 -O2 -g -fPIC -Wall -Wextra -Wno-unused-result -ffp-contra
 NVFLAGS  := -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a \
             -Xcompiler -fPIC -Iinclude -I$(HOSTDIR)
 
-HOST_SRC := input.c geometry.c voxels.c tables.c ranecu_host.c report.c dose.c api.c
+HOST_SRC := input.c geometry.c voxels.c tables.c ranecu_host.c report.c dose.c api.c post.c
 HOST_OBJ := $(HOST_SRC:%.c=$(BUILD)/%.o)
-CUDA_OBJ := $(BUILD)/device.o $(BUILD)/launch_exact.o $(BUILD)/launch_fast.o
+CUDA_OBJ := $(BUILD)/device.o $(BUILD)/postprocess.o $(BUILD)/launch_exact.o $(BUILD)/launch_fast.o
 CUDA_HDR := $(CUDADIR)/transport.cuh $(CUDADIR)/regroup.cuh $(CUDADIR)/wavefront.cuh $(CUDADIR)/scene_dev.h $(CUDADIR)/device_internal.h $(HOSTDIR)/mcgpu_host.h
 
 all: lib exe oracle
@@ -33,6 +33,10 @@ $(BUILD)/%.o: $(HOSTDIR)/%.c $(HOSTDIR)/mcgpu_host.h include/mcgpu_b200.h
 	$(CC) $(CFLAGS) -c $< -o $@
 
 $(BUILD)/device.o: $(CUDADIR)/device.cu $(CUDA_HDR)
+	@mkdir -p $(BUILD)
+	$(NVCC) $(NVFLAGS) -fmad=false -c $< -o $@
+
+$(BUILD)/postprocess.o: $(CUDADIR)/postprocess.cu $(CUDA_HDR)
 	@mkdir -p $(BUILD)
 	$(NVCC) $(NVFLAGS) -fmad=false -c $< -o $@
 

@@ -131,6 +131,25 @@ int mcgpu_write_projection_ascii(mcgpu_ctx* ctx, int p, const uint64_t* image, d
  * ASCII columns (the reference's own .raw writer is commented out, H:2911-2949).  mcgpu_run_all writes it
  * next to every ASCII file when the environment has MCGPU_WRITE_RAW=1. */
 int mcgpu_write_projection_raw(mcgpu_ctx* ctx, int p, const uint64_t* image);
+/* ---- projection post-processing on the device -------------------------------------------------
+ * What cbctmc computes in NumPy/SciPy after the simulation, from the u64 tallies instead of the text files.
+ *
+ * mcgpu_post_intensity: the float32 images MCProjection._read_raw (cbctmc/mc/projection.py:36-51) would obtain
+ * from the ASCII file of this tally -- the values "%.8lf" prints and np.loadtxt reads back, detector rows flipped,
+ * x cropped to crop_x (n_detector_pixels_half_fan[0] = 1024; <= 0: no crop) -- summed like projections_to_itk
+ * (projection.py:143-149): total = sum of the 4 planes, unscattered = plane 0, scattered = planes 1..3.  Outputs
+ * are host arrays [Nz][crop_x] (any may be NULL); min_positive[3] receives the smallest positive value of each
+ * (for the stack-wide `min_non_zero`, projection.py:151).  tally == NULL: use the tally of the projection
+ * simulated last on device 0 (no host round trip).  launched_histories = mcgpu_info.launched_histories. */
+int mcgpu_post_intensity(mcgpu_ctx* ctx, const uint64_t* tally, unsigned long long launched_histories, int crop_x, float* total, float* unscattered, float* scattered,
+                         float* min_positive);
+/* scipy.ndimage.gaussian_filter(in[n0][n1] float32, sigma=(sigma0, sigma1)) as normalize_projections applies it to
+ * the air image (projection.py:108-111; sigma (10, 10) in simulation.py:241): mode 'reflect', truncate 4.0. */
+int mcgpu_post_gaussian(mcgpu_ctx* ctx, const float* in, int n0, int n1, double sigma0, double sigma1, float* out);
+/* In place on stack[n_images][n0][n1]: zeros -> min_nonzero (projection.py:153), then log(air / p) in float32
+ * (normalize_projections, projection.py:119-120). */
+int mcgpu_post_normalize(mcgpu_ctx* ctx, const float* air, float* stack, long long n_images, int n0, int n1, float min_nonzero);
+
 /* Name report_image gives the file of projection p; returns strlen or <0. */
 int mcgpu_projection_filename(const mcgpu_ctx* ctx, int p, char* out, size_t out_len);
 
