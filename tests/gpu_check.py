@@ -3,7 +3,7 @@
 source (oracle/_ref/MC-GPU_v1.3_sm100_exact.x) and a first timing next to the reference's
 shipped-flags build.  Writes a JSON summary to gpurun_out/gpu_check.json.
 
-Usage: python tools/gpu_check.py [--big]"""
+Usage: python tests/gpu_check.py [--big]"""
 import json
 import re
 import subprocess

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Post-processing at the reference size (GPU box): 1848x768 tallies of a short thorax scan -> cropped float32
 stacks + air normalisation on the device (mcgpu_post_*), next to the reference's route (ASCII file ->
-np.loadtxt -> NumPy/SciPy, restated in oracle/post_oracle.py) on the same data.  Usage: python tools/post_bench.py [P]"""
+np.loadtxt -> NumPy/SciPy, restated in oracle/post_oracle.py) on the same data.  Usage: python tests/post_bench.py [P]"""
 import json
 import sys
 import tempfile

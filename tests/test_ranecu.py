@@ -41,7 +41,7 @@ def test_projection_seed_advance_matches_update_seed(pkg, oracle_py):
     seed = 42
     for launched in (10_003_200, 595_180_800, 11_905_920_000, 50_003_200_000):
         assert pkg.engine.advance_projection_seed(seed, launched) == L.oracle_update_seed(1, launched, seed)
-    # the reference log of the first GPU run (tools/gpu_check.py, 200 006 400 histories, seed 42)
+    # the reference log of the first GPU run (tests/gpu_check.py, 200 006 400 histories, seed 42)
     assert pkg.engine.advance_projection_seed(42, 200_006_400) == 657632199
 
 
