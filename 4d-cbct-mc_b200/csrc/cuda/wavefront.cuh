@@ -6,7 +6,7 @@
 // kernel is issue-bound, so idle lanes are the loss that is left.
 //
 // How: a CTA of 16 warps owns a POOL of photon contexts in shared memory (2 per thread; a context
-// = one RANECU stream and the photon it is tracking, 12 words) and four queues of context ids, one
+// = one RANECU stream and the photon it is tracking, 12 words at an odd stride of 13) and four queues of context ids, one
 // per kind of work:
 //   Q_W  delta-tracking steps                       Q_N  tally / next stream / next history (source)
 //   Q_C  Compton (S0 for fresh events + one tau trial)   Q_R  Rayleigh
@@ -22,6 +22,12 @@
 // `avail` counts published entries and is claimed with atomicCAS by the popping warp, `head` gives
 // it its ring positions.  No locks; the only waits are on an entry that is reserved but not yet
 // written, and they are bounded (a watchdog raises the launch's error flag instead of hanging).
+//
+// Code size is a first-class constraint here: with exact arithmetic the kernel was bound by instruction-
+// cache misses until its hot code fitted the SM's 32 KB instruction cache.  Hence ONE
+// scheduling policy (sticky: a CTA drains the queue it is on), ONE context load/store site for every kind
+// of batch, ONE cooperative shell-term call site for S0 and S(tau), rolled loops.  Measure
+// sm__icc_request_hit_rate / gcc__cache_requests_type_instruction (tools/icc_probe.sh) after any change.
 #pragma once
 #include "regroup.cuh"
 
