@@ -72,6 +72,18 @@ static int gaussian_weights(double sigma, double** w_out) {
   return radius;
 }
 
+int mcgpu_gaussian_weights(double sigma, double* w, int capacity) {
+  double* tmp = NULL;
+  int r, i;
+  if (!(sigma > 1e-15)) return MCGPU_E_ARG;
+  r = gaussian_weights(sigma, &tmp);
+  if (r < 0) return MCGPU_E_NOMEM;
+  if (w)
+    for (i = 0; i <= r && i < capacity; i++) w[i] = tmp[i];
+  free(tmp);
+  return r;
+}
+
 int mcgpu_post_gaussian(mcgpu_ctx* ctx, const float* in, int n0, int n1, double sigma0, double sigma1, float* out) {
   double *w0 = NULL, *w1 = NULL;
   int r0 = 0, r1 = 0, rc;

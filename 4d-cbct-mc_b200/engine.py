@@ -56,6 +56,7 @@ _SIGS = {
     "mcgpu_write_projection_raw": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "mcgpu_post_intensity": (C.c_int, [C.c_void_p, C.c_void_p, C.c_ulonglong, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mcgpu_post_gaussian": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p]),
+    "mcgpu_gaussian_weights": (C.c_int, [C.c_double, C.c_void_p, C.c_int]),
     "mcgpu_post_normalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_float]),
     "mcgpu_projection_filename": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_size_t]),
     "mcgpu_reset_dose": (C.c_int, [C.c_void_p]),
@@ -239,6 +240,15 @@ class Engine:
         out = np.empty_like(a)
         self._check(_lib.mcgpu_post_gaussian(self._h, a.ctypes.data, a.shape[0], a.shape[1], float(sigma[0]), float(sigma[1]), out.ctypes.data))
         return out
+
+    @staticmethod
+    def gaussian_weights(sigma: float) -> np.ndarray:
+        r = _lib.mcgpu_gaussian_weights(float(sigma), None, 0)
+        if r < 0:
+            raise McgpuError(r, "gaussian_weights: sigma must be positive")
+        w = np.empty(r + 1, dtype=np.float64)
+        _lib.mcgpu_gaussian_weights(float(sigma), w.ctypes.data, r + 1)
+        return w
 
     def post_normalize(self, air: np.ndarray, stack: np.ndarray, min_nonzero: float) -> np.ndarray:
         """In place on a C-contiguous float32 stack [P][Nz][Nx]."""
