@@ -148,7 +148,7 @@ int mcgpu_post_intensity(mcgpu_ctx* ctx, const uint64_t* tally, unsigned long lo
 int mcgpu_post_gaussian(mcgpu_ctx* ctx, const float* in, int n0, int n1, double sigma0, double sigma1, float* out);
 /* The kernel mcgpu_post_gaussian uses for one axis: w[k], k = 0..radius, the weight at distance k of
  * scipy.ndimage's _gaussian_kernel1d(sigma, 0, radius = int(4 sigma + 0.5)) -- same formula and summation order, equal to
- * within 1 ulp of float64 (libm exp vs NumPy's SIMD exp); host only.  Returns the radius. */
+ * within 2 ulp of float64 (libm exp vs NumPy's SIMD exp); host only.  Returns the radius. */
 int mcgpu_gaussian_weights(double sigma, double* w, int capacity);
 /* In place on stack[n_images][n0][n1]: zeros -> min_nonzero (projection.py:153), then log(air / p) in float32
  * (normalize_projections, projection.py:119-120). */
