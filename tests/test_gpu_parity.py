@@ -161,6 +161,19 @@ def test_run_all_writes_the_reference_file_set(pkg, gpu_engine_factory, tmp_path
     eng.close()
 
 
+def test_run_all_writes_the_binary_side_files_on_request(pkg, gpu_engine_factory, tmp_path, monkeypatch):
+    inp, cfg, _ = build_case(pkg, "thorax_p4", tmp_path)
+    monkeypatch.setenv("MCGPU_WRITE_RAW", "1")
+    eng = gpu_engine_factory(inp)
+    eng.run_all()
+    for p in range(4):
+        name = eng.projection_filename(p)
+        raw = pkg.mcio.read_projection_raw(name + ".raw", cfg.n_detector_pixels)
+        txt = pkg.mcio.read_projection(name, cfg.n_detector_pixels)
+        assert raw.sum() > 0 and np.allclose(raw, txt, rtol=1e-6, atol=1e-8)
+    eng.close()
+
+
 def test_executable_is_a_drop_in(pkg, gpu_engine_factory, tmp_path):
     inp, cfg, _ = build_case(pkg, "thorax_p4", tmp_path)
     exe = ROOT / "4d-cbct-mc_b200" / "bin" / "MC-GPU_v1.3.x"
