@@ -205,6 +205,39 @@ static void* vox_worker(void* arg) {
   }
 }
 
+/* Binary geometry ("optional binary .voxb emitted by the Python side"; mcio.write_voxb): little-endian
+ *   char magic[8] = "MCGPUVXB"; uint32 version = 1; uint32 nx, ny, nz; float32 dx, dy, dz [cm];
+ *   uint8 material[nx*ny*nz] (1-based, x fastest); float32 density[nx*ny*nz]
+ * optionally gzip-compressed.  Same validation and the same volume as the text file with these values. */
+static int read_voxels_binary(mcgpu_ctx* ctx, gzFile f) {
+  uint32_t head[4];
+  float size[3];
+  size_t n, done = 0;
+  int rc;
+  if (gzread(f, head, sizeof head) != (int)sizeof head || gzread(f, size, sizeof size) != (int)sizeof size)
+    return mcgpu_fail(ctx, MCGPU_E_PARSE, "load_voxels: truncated binary geometry header");
+  if (head[0] != 1u) return mcgpu_fail(ctx, MCGPU_E_PARSE, "load_voxels: unsupported binary geometry version %u", head[0]);
+  if ((rc = alloc_volume(ctx, (int)head[1], (int)head[2], (int)head[3], size)) != MCGPU_OK) return rc;
+  n = (size_t)head[1] * head[2] * head[3];
+  while (done < n) { /* gzread takes at most INT_MAX bytes per call */
+    const size_t want = n - done < ((size_t)1 << 28) ? n - done : ((size_t)1 << 28);
+    if (gzread(f, ctx->vol.material + done, (unsigned)want) != (int)want) return mcgpu_fail(ctx, MCGPU_E_PARSE, "load_voxels: binary geometry ends inside the material array");
+    done += want;
+  }
+  for (done = 0; done < n;) {
+    const size_t want = n - done < ((size_t)1 << 26) ? n - done : ((size_t)1 << 26);
+    if (gzread(f, ctx->vol.density + done, (unsigned)(want * sizeof(float))) != (int)(want * sizeof(float)))
+      return mcgpu_fail(ctx, MCGPU_E_PARSE, "load_voxels: binary geometry ends inside the density array");
+    done += want;
+  }
+  for (done = 0; done < n; done++) { /* the checks of load_voxels (H:2120-2132) */
+    if (ctx->vol.material[done] > MCGPU_MAX_MATERIALS || ctx->vol.material[done] < 1)
+      return mcgpu_fail(ctx, MCGPU_E_PARSE, "load_voxels: voxel material number %d out of range [1,%d] at voxel number %zu", ctx->vol.material[done], MCGPU_MAX_MATERIALS, done + 1);
+    if (ctx->vol.density[done] < 1.0e-9f) return mcgpu_fail(ctx, MCGPU_E_PARSE, "load_voxels: voxel density can not be 0 or negative at voxel number %zu", done + 1);
+  }
+  return mcgpu_finish_volume(ctx);
+}
+
 int mcgpu_read_voxels(mcgpu_ctx* ctx, const char* path) {
   char line[MCGPU_LINE];
   int nx = 0, ny = 0, nz = 0, rc = MCGPU_OK, n_threads, i, eof = 0;
@@ -219,6 +252,15 @@ int mcgpu_read_voxels(mcgpu_ctx* ctx, const char* path) {
   gzFile f = gzopen(path, "rb");
   if (!f) return mcgpu_fail(ctx, MCGPU_E_PARSE, "load_voxels: file '%s' does not exist", path);
   gzbuffer(f, 1 << 20);
+  {
+    char magic[8];
+    if (gzread(f, magic, 8) == 8 && !memcmp(magic, "MCGPUVXB", 8)) {
+      rc = read_voxels_binary(ctx, f);
+      gzclose(f);
+      return rc;
+    }
+    gzrewind(f);
+  }
   do {
     if (!gzgets(f, line, MCGPU_LINE)) {
       gzclose(f);

@@ -235,6 +235,24 @@ def read_projection(path: Path, n_pixels: tuple[int, int]) -> np.ndarray:
     return data.reshape(nz, nx, 4).transpose(2, 0, 1).copy()
 
 
+def write_voxb(path: Path, materials: np.ndarray, densities: np.ndarray, spacing_cm, compress: bool = False) -> Path:
+    """Binary geometry the engine reads without tokenising text (csrc/host/voxels.c: read_voxels_binary).  Same
+    arguments as write_vox: arrays indexed [x, y, z], materials 1-based; stored x fastest like the text file."""
+    import struct
+
+    assert materials.shape == densities.shape and materials.ndim == 3
+    nx, ny, nz = materials.shape
+    m = np.ascontiguousarray(materials.transpose(2, 1, 0), dtype=np.uint8)
+    d = np.ascontiguousarray(densities.transpose(2, 1, 0), dtype="<f4")
+    head = b"MCGPUVXB" + struct.pack("<4I3f", 1, nx, ny, nz, *[float(s) for s in spacing_cm])
+    opener = gzip.open if compress else open
+    with opener(path, "wb") as f:
+        f.write(head)
+        f.write(m.tobytes())
+        f.write(d.tobytes())
+    return Path(path)
+
+
 def read_projection_raw(path: Path, n_pixels: tuple[int, int]) -> np.ndarray:
     """Binary side-file (mcgpu_write_projection_raw): float32 [4, Nz, Nx], same values as the ASCII columns."""
     nx, nz = n_pixels

@@ -194,3 +194,32 @@ def test_large_file_spans_many_blocks_and_ignores_trailing_lines(pkg, cases, tmp
         assert np.array_equal(eng.table("voxel_material").reshape(60, 96, 96), ph.materials.transpose(2, 1, 0))
         want = np.array([float("%.6f" % d) for d in np.unique(ph.densities)], dtype=np.float32)
         assert set(np.unique(eng.table("voxel_density")).tolist()) == set(want.tolist())
+
+
+def test_binary_geometry_gives_the_same_volume_as_the_text_file(pkg, cases, tmp_path):
+    """.voxb: same packed voxels, palette and density maxima as the .vox.gz of the same arrays"""
+    inp, cfg, ph = cases["thorax_p4"]
+    with pkg.engine.Engine() as eng:
+        eng.load_input(inp).load_voxels()
+        ref = {t: eng.table(t).copy() for t in ("voxel_packed", "voxel_material", "voxel_density")}
+        ref_info = eng.info
+    for compress in (False, True):
+        f = pkg.mcio.write_voxb(tmp_path / f"g{int(compress)}.voxb", ph.materials, ph.densities, ph.spacing_cm, compress=compress)
+        with pkg.engine.Engine() as eng:
+            eng.load_input(inp).load_voxels(f)
+            for t, a in ref.items():
+                assert np.array_equal(eng.table(t), a), t
+            i = eng.info
+            assert (i.num_voxels_x, i.num_voxels_y, i.num_voxels_z, i.voxel_bits, i.palette_size) == (
+                ref_info.num_voxels_x, ref_info.num_voxels_y, ref_info.num_voxels_z, ref_info.voxel_bits, ref_info.palette_size)
+    raw = (tmp_path / "g0.voxb").read_bytes()
+    (tmp_path / "short.voxb").write_bytes(raw[: len(raw) // 2])
+    bad = bytearray(raw)
+    bad[36] = 77  # first material byte
+    (tmp_path / "bad.voxb").write_bytes(bytes(bad))
+    with pkg.engine.Engine() as eng:
+        eng.load_input(inp)
+        with pytest.raises(pkg.engine.McgpuError, match="ends inside"):
+            eng.load_voxels(tmp_path / "short.voxb")
+        with pytest.raises(pkg.engine.McgpuError, match="out of range"):
+            eng.load_voxels(tmp_path / "bad.voxb")
