@@ -6,8 +6,10 @@
  * kernel's constants.  Table LAYOUT on the device is our own (mcgpu_build_scene): compacted to
  * the materials present, one 32-byte record per (energy bin, material). */
 #include <math.h>
+#include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include "mcgpu_host.h"
@@ -110,13 +112,175 @@ static int seek_gz(gzFile f, const char* tag, char* line) {
   return 1;
 }
 
+/* One material file.  Everything it writes is private to the material (its column of the tables, its
+ * Woodcock candidates in `wood`, its energy step), so the files are parsed concurrently; material 1 goes
+ * first on its own because it allocates the tables and defines the energy grid (H:2240-2285). */
+typedef struct {
+  mcgpu_tables* t;
+  float* density_max;
+  const char* path;
+  int mat;
+  float* wood;     /* [num_values] total MFP * rho_nominal / rho_max of this material, or NULL when not loaded */
+  double delta_e;  /* energy step read from this file */
+  int loaded, rc;
+  char err[MCGPU_LINE + 160];
+} material_job;
+
+#define MFAIL(code, ...)                      \
+  do {                                        \
+    if (f) gzclose(f);                        \
+    snprintf(j->err, sizeof j->err, __VA_ARGS__); \
+    j->rc = (code);                           \
+    return;                                   \
+  } while (0)
+
+static void load_one_material(material_job* j) {
+  mcgpu_tables* t = j->t;
+  const int mat = j->mat;
+  const size_t NR = (size_t)MCGPU_NP_RAYLEIGH * MCGPU_MAX_MATERIALS;
+  char line[MCGPU_LINE];
+  int n_values = 0, n_rayleigh = 0, n_shells = 0, i;
+  double e_last = -1.0, delta_e = -99999.0;
+  gzFile f = gzopen(j->path, "rb");
+  j->rc = MCGPU_OK;
+  j->loaded = 0;
+  if (!f) MFAIL(MCGPU_E_PARSE, "load_material: file %d '%s' does not exist", mat, j->path);
+  gzbuffer(f, 1 << 18);
+  if (!seek_gz(f, "[NOMINAL DENSITY", line)) MFAIL(MCGPU_E_PARSE, "load_material: '%s' does not contain the string '[NOMINAL DENSITY'", j->path);
+  gzgets(f, line, MCGPU_LINE);
+  sscanf(line, "# %f", &t->density_nominal[mat]);
+
+  if (!(j->density_max[mat] > 0)) { /* not in the voxels: only material 1 is read in full (H:2224-2233) */
+    if (mat == 0)
+      j->density_max[mat] = 0.01f * t->density_nominal[mat];
+    else {
+      gzclose(f);
+      return;
+    }
+  }
+
+  gzgets(f, line, MCGPU_LINE);
+  gzgets(f, line, MCGPU_LINE);
+  sscanf(line, "# %d", &n_values);
+  if (mat == 0) {
+    if (n_values < 2 || n_values > MCGPU_MAX_ENERGYBINS_RAYLEIGH)
+      MFAIL(MCGPU_E_PARSE, "load_material: unsupported number of energy bins %d (max %d)", n_values, MCGPU_MAX_ENERGYBINS_RAYLEIGH);
+    t->num_values = n_values;
+    t->woodcock = (mcgpu_f2*)calloc(n_values, sizeof(mcgpu_f2));
+    t->mfp_a = (mcgpu_f3*)calloc((size_t)n_values * MCGPU_MAX_MATERIALS, sizeof(mcgpu_f3));
+    t->mfp_b = (mcgpu_f3*)calloc((size_t)n_values * MCGPU_MAX_MATERIALS, sizeof(mcgpu_f3));
+    t->ray_pmax = (float*)calloc((size_t)(n_values + 1) * MCGPU_MAX_MATERIALS, sizeof(float)); /* zero row nE: Q3 */
+    t->ray_xco = (float*)calloc(NR, sizeof(float));
+    t->ray_pco = (float*)calloc(NR, sizeof(float));
+    t->ray_aco = (float*)calloc(NR, sizeof(float));
+    t->ray_bco = (float*)calloc(NR, sizeof(float));
+    t->ray_itlco = (uint8_t*)calloc(NR, 1);
+    t->ray_ituco = (uint8_t*)calloc(NR, 1);
+    if (!t->woodcock || !t->mfp_a || !t->mfp_b || !t->ray_pmax || !t->ray_xco || !t->ray_pco || !t->ray_aco || !t->ray_bco || !t->ray_itlco || !t->ray_ituco)
+      MFAIL(MCGPU_E_NOMEM, "load_material: not enough memory for the interpolation tables");
+  } else if (n_values != t->num_values)
+    MFAIL(MCGPU_E_PARSE, "load_material: incorrect number of energy values in material '%s': input=%d, expected=%d", j->path, n_values, t->num_values);
+  j->wood = (float*)malloc(sizeof(float) * (size_t)n_values);
+  if (!j->wood) MFAIL(MCGPU_E_NOMEM, "load_material: not enough memory for the interpolation tables");
+
+  /* -- mean free paths -> inverse MFP per unit density at the bin edges (H:2287-2332) */
+  gzgets(f, line, MCGPU_LINE);
+  gzgets(f, line, MCGPU_LINE);
+  for (i = 0; i < n_values; i++) {
+    double e = 0, ray = 0, com = 0, pho = 0, tot = 0, pmax = 0;
+    mcgpu_f3* a = &t->mfp_a[(size_t)i * MCGPU_MAX_MATERIALS + mat];
+    if (!gzgets(f, line, MCGPU_LINE)) MFAIL(MCGPU_E_PARSE, "load_material: '%s' ends inside the mean free path table", j->path);
+    sscanf(line, "  %le  %le  %le  %le  %le  %le", &e, &ray, &com, &pho, &tot, &pmax);
+    j->wood[i] = tot * (t->density_nominal[mat]) / (j->density_max[mat]); /* the Woodcock candidate of this material (H:2294-2296) */
+    a->x = 1.0 / (tot * t->density_nominal[mat]);
+    a->y = 1.0 / (com * t->density_nominal[mat]);
+    a->z = 1.0 / (ray * t->density_nominal[mat]);
+    t->ray_pmax[(size_t)i * MCGPU_MAX_MATERIALS + mat] = pmax;
+    if (i == 0 && mat == 0) t->e0 = e;
+    if (i == 0) {
+      if (fabs(e - t->e0) > 1.0e-9) MFAIL(MCGPU_E_PARSE, "load_material: incorrect first energy value in material '%s': input=%f, expected=%f", j->path, e, t->e0);
+    } else if (i == 1)
+      delta_e = e - e_last;
+    else if (((fabs((e - e_last) - delta_e)) / delta_e) > 0.001)
+      MFAIL(MCGPU_E_PARSE, "load_material: the energy step between mean free path values is not constant (material '%s', value %d)", j->path, i);
+    e_last = e;
+  }
+  j->delta_e = delta_e;
+
+  /* -- slopes, then re-base the intercepts to E=0 (H:2340-2358) */
+  for (i = 0; i < n_values - 1; i++) {
+    const size_t bin = (size_t)i * MCGPU_MAX_MATERIALS + mat;
+    t->mfp_b[bin].x = (t->mfp_a[bin + MCGPU_MAX_MATERIALS].x - t->mfp_a[bin].x) / delta_e;
+    t->mfp_b[bin].y = (t->mfp_a[bin + MCGPU_MAX_MATERIALS].y - t->mfp_a[bin].y) / delta_e;
+    t->mfp_b[bin].z = (t->mfp_a[bin + MCGPU_MAX_MATERIALS].z - t->mfp_a[bin].z) / delta_e;
+  }
+  t->mfp_b[(size_t)(n_values - 1) * MCGPU_MAX_MATERIALS + mat] = t->mfp_b[(size_t)(n_values - 2) * MCGPU_MAX_MATERIALS + mat];
+  for (i = 0; i < n_values; i++) {
+    const size_t bin = (size_t)i * MCGPU_MAX_MATERIALS + mat;
+    const double e = t->e0 + i * delta_e;
+    t->mfp_a[bin].x = t->mfp_a[bin].x - e * t->mfp_b[bin].x;
+    t->mfp_a[bin].y = t->mfp_a[bin].y - e * t->mfp_b[bin].y;
+    t->mfp_a[bin].z = t->mfp_a[bin].z - e * t->mfp_b[bin].z;
+  }
+
+  /* -- Rayleigh RITA grid (H:2361-2394) */
+  if (!seek_gz(f, "[DATA VALUES", line)) MFAIL(MCGPU_E_PARSE, "load_material: Rayleigh data not found in file '%s'", j->path);
+  gzgets(f, line, MCGPU_LINE);
+  sscanf(line, "# %d", &n_rayleigh);
+  if (n_rayleigh != MCGPU_NP_RAYLEIGH) MFAIL(MCGPU_E_PARSE, "load_material: %d Rayleigh sampling values in '%s', expected %d", n_rayleigh, j->path, MCGPU_NP_RAYLEIGH);
+  gzgets(f, line, MCGPU_LINE);
+  for (i = 0; i < n_rayleigh; i++) {
+    const int bin = MCGPU_NP_RAYLEIGH * mat + i;
+    int itl = 0, itu = 0;
+    gzgets(f, line, MCGPU_LINE);
+    sscanf(line, "  %e  %e  %e  %e  %d  %d", &t->ray_xco[bin], &t->ray_pco[bin], &t->ray_aco[bin], &t->ray_bco[bin], &itl, &itu);
+    t->ray_itlco[bin] = (uint8_t)itl;
+    t->ray_ituco[bin] = (uint8_t)itu;
+  }
+
+  /* -- Compton shells (H:2398-2426) */
+  if (!seek_gz(f, "[NUMBER OF SHELLS", line)) MFAIL(MCGPU_E_PARSE, "load_material: Compton data not found in file '%s'", j->path);
+  gzgets(f, line, MCGPU_LINE);
+  sscanf(line, "# %d", &n_shells);
+  if (n_shells > MCGPU_MAX_SHELLS || n_shells < 0) MFAIL(MCGPU_E_PARSE, "load_material: too many Compton shells in '%s': %d (max %d)", j->path, n_shells, MCGPU_MAX_SHELLS);
+  t->cmp_noscco[mat] = n_shells;
+  gzgets(f, line, MCGPU_LINE);
+  for (i = 0; i < n_shells; i++) {
+    const int bin = mat + i * MCGPU_MAX_MATERIALS;
+    int kz, ks;
+    gzgets(f, line, MCGPU_LINE);
+    sscanf(line, " %e  %e  %e  %d  %d", &t->cmp_fco[bin], &t->cmp_uico[bin], &t->cmp_fj0[bin], &kz, &ks);
+  }
+  gzclose(f);
+  t->material_loaded[mat] = 1;
+  j->loaded = 1;
+}
+#undef MFAIL
+
+typedef struct {
+  material_job* jobs;
+  int n, next;
+  pthread_mutex_t mu;
+} material_pool;
+
+static void* material_worker(void* arg) {
+  material_pool* p = (material_pool*)arg;
+  for (;;) {
+    int k;
+    pthread_mutex_lock(&p->mu);
+    k = p->next < p->n ? p->next++ : -1;
+    pthread_mutex_unlock(&p->mu);
+    if (k < 0) return NULL;
+    load_one_material(&p->jobs[k]);
+  }
+}
+
 int mcgpu_read_materials(mcgpu_ctx* ctx, const char* const* paths, int n_paths) {
   mcgpu_tables* t = &ctx->tab;
   float* density_max = ctx->vol.density_max;
-  char line[MCGPU_LINE];
+  material_job jobs[MCGPU_MAX_MATERIALS];
   double delta_e = -99999.0;
-  int mat, i;
-  const size_t NR = (size_t)MCGPU_NP_RAYLEIGH * MCGPU_MAX_MATERIALS;
+  int mat, i, n_jobs = 0, rc = MCGPU_OK;
 
   mcgpu_free_tables(t);
   for (mat = 0; mat < MCGPU_MAX_MATERIALS; mat++) t->density_nominal[mat] = -1.0f;
@@ -130,131 +294,47 @@ int mcgpu_read_materials(mcgpu_ctx* ctx, const char* const* paths, int n_paths) 
     return mcgpu_fail(ctx, MCGPU_E_PARSE, "load_material: the first material file is required (it defines the energy grid)");
 
   for (mat = 0; mat < n_paths; mat++) {
-    int n_values = 0, n_rayleigh = 0, n_shells = 0;
-    double e_last = -1.0;
-    gzFile f;
+    material_job* j;
     if (!paths[mat] || paths[mat][0] == '\0' || paths[mat][0] == '\n') continue;
-    f = gzopen(paths[mat], "rb");
-    if (!f) return mcgpu_fail(ctx, MCGPU_E_PARSE, "load_material: file %d '%s' does not exist", mat, paths[mat]);
-    gzbuffer(f, 1 << 18);
-#define MBAIL(...)                                      \
-  do {                                                  \
-    gzclose(f);                                         \
-    return mcgpu_fail(ctx, MCGPU_E_PARSE, __VA_ARGS__); \
-  } while (0)
-    if (!seek_gz(f, "[NOMINAL DENSITY", line)) MBAIL("load_material: '%s' does not contain the string '[NOMINAL DENSITY'", paths[mat]);
-    gzgets(f, line, MCGPU_LINE);
-    sscanf(line, "# %f", &t->density_nominal[mat]);
+    j = &jobs[n_jobs++];
+    memset(j, 0, sizeof *j);
+    j->t = t, j->density_max = density_max, j->path = paths[mat], j->mat = mat;
+  }
+  load_one_material(&jobs[0]); /* material 1: allocates the tables, fixes the energy grid */
+  if (jobs[0].rc == MCGPU_OK && n_jobs > 1) {
+    material_pool pool;
+    pthread_t threads[8];
+    int n_threads = (int)sysconf(_SC_NPROCESSORS_ONLN), k;
+    if (n_threads > 8) n_threads = 8;
+    if (n_threads > n_jobs - 1) n_threads = n_jobs - 1;
+    if (n_threads < 1) n_threads = 1;
+    pool.jobs = jobs + 1, pool.n = n_jobs - 1, pool.next = 0;
+    pthread_mutex_init(&pool.mu, NULL);
+    for (k = 0; k < n_threads; k++)
+      if (pthread_create(&threads[k], NULL, material_worker, &pool) != 0) break;
+    if (k == 0) material_worker(&pool); /* no thread could be started: do the work here */
+    while (k-- > 0) pthread_join(threads[k], NULL);
+    pthread_mutex_destroy(&pool.mu);
+  }
 
-    if (!(density_max[mat] > 0)) { /* not in the voxels: only material 1 is read in full (H:2224-2233) */
-      if (mat == 0)
-        density_max[mat] = 0.01f * t->density_nominal[mat];
-      else {
-        gzclose(f);
-        continue;
-      }
-    }
-
-    gzgets(f, line, MCGPU_LINE);
-    gzgets(f, line, MCGPU_LINE);
-    sscanf(line, "# %d", &n_values);
-    if (mat == 0) {
-      if (n_values < 2 || n_values > MCGPU_MAX_ENERGYBINS_RAYLEIGH)
-        MBAIL("load_material: unsupported number of energy bins %d (max %d)", n_values, MCGPU_MAX_ENERGYBINS_RAYLEIGH);
-      t->num_values = n_values;
-      t->woodcock = (mcgpu_f2*)calloc(n_values, sizeof(mcgpu_f2));
-      t->mfp_a = (mcgpu_f3*)calloc((size_t)n_values * MCGPU_MAX_MATERIALS, sizeof(mcgpu_f3));
-      t->mfp_b = (mcgpu_f3*)calloc((size_t)n_values * MCGPU_MAX_MATERIALS, sizeof(mcgpu_f3));
-      t->ray_pmax = (float*)calloc((size_t)(n_values + 1) * MCGPU_MAX_MATERIALS, sizeof(float)); /* zero row nE: Q3 */
-      t->ray_xco = (float*)calloc(NR, sizeof(float));
-      t->ray_pco = (float*)calloc(NR, sizeof(float));
-      t->ray_aco = (float*)calloc(NR, sizeof(float));
-      t->ray_bco = (float*)calloc(NR, sizeof(float));
-      t->ray_itlco = (uint8_t*)calloc(NR, 1);
-      t->ray_ituco = (uint8_t*)calloc(NR, 1);
-      if (!t->woodcock || !t->mfp_a || !t->mfp_b || !t->ray_pmax || !t->ray_xco || !t->ray_pco || !t->ray_aco || !t->ray_bco || !t->ray_itlco || !t->ray_ituco) {
-        gzclose(f);
-        return mcgpu_fail(ctx, MCGPU_E_NOMEM, "load_material: not enough memory for the interpolation tables");
-      }
-      for (i = 0; i < n_values; i++) t->woodcock[i].x = 99999999.99f;
-    } else if (n_values != t->num_values)
-      MBAIL("load_material: incorrect number of energy values in material '%s': input=%d, expected=%d", paths[mat], n_values, t->num_values);
-
-    /* -- mean free paths -> inverse MFP per unit density at the bin edges (H:2287-2332) */
-    gzgets(f, line, MCGPU_LINE);
-    gzgets(f, line, MCGPU_LINE);
-    for (i = 0; i < n_values; i++) {
-      double e = 0, ray = 0, com = 0, pho = 0, tot = 0, pmax = 0;
-      float w;
-      mcgpu_f3* a = &t->mfp_a[(size_t)i * MCGPU_MAX_MATERIALS + mat];
-      if (!gzgets(f, line, MCGPU_LINE)) MBAIL("load_material: '%s' ends inside the mean free path table", paths[mat]);
-      sscanf(line, "  %le  %le  %le  %le  %le  %le", &e, &ray, &com, &pho, &tot, &pmax);
-      w = tot * (t->density_nominal[mat]) / (density_max[mat]);
-      if (w < t->woodcock[i].x) t->woodcock[i].x = w;
-      a->x = 1.0 / (tot * t->density_nominal[mat]);
-      a->y = 1.0 / (com * t->density_nominal[mat]);
-      a->z = 1.0 / (ray * t->density_nominal[mat]);
-      t->ray_pmax[(size_t)i * MCGPU_MAX_MATERIALS + mat] = pmax;
-      if (i == 0 && mat == 0) t->e0 = e;
-      if (i == 0) {
-        if (fabs(e - t->e0) > 1.0e-9) MBAIL("load_material: incorrect first energy value in material '%s': input=%f, expected=%f", paths[mat], e, t->e0);
-      } else if (i == 1)
-        delta_e = e - e_last;
-      else if (((fabs((e - e_last) - delta_e)) / delta_e) > 0.001)
-        MBAIL("load_material: the energy step between mean free path values is not constant (material '%s', value %d)", paths[mat], i);
-      e_last = e;
+  /* results in material order: first error wins; Woodcock minimum over the loaded materials (H:2294-2296);
+   * the energy step the tables keep is the one of the last material read, as in the reference's loop */
+  for (i = 0; i < n_jobs && rc == MCGPU_OK; i++)
+    if (jobs[i].rc != MCGPU_OK) rc = mcgpu_fail(ctx, jobs[i].rc, "%s", jobs[i].err);
+  if (rc == MCGPU_OK) {
+    for (i = 0; i < t->num_values; i++) t->woodcock[i].x = 99999999.99f;
+    for (i = 0; i < n_jobs; i++) {
+      int k;
+      if (!jobs[i].loaded) continue;
+      for (k = 0; k < t->num_values; k++)
+        if (jobs[i].wood[k] < t->woodcock[k].x) t->woodcock[k].x = jobs[i].wood[k];
+      delta_e = jobs[i].delta_e;
     }
     t->ide = 1.0f / delta_e;
     t->delta_e = delta_e;
-
-    /* -- slopes, then re-base the intercepts to E=0 (H:2340-2358) */
-    for (i = 0; i < n_values - 1; i++) {
-      const size_t bin = (size_t)i * MCGPU_MAX_MATERIALS + mat;
-      t->mfp_b[bin].x = (t->mfp_a[bin + MCGPU_MAX_MATERIALS].x - t->mfp_a[bin].x) / delta_e;
-      t->mfp_b[bin].y = (t->mfp_a[bin + MCGPU_MAX_MATERIALS].y - t->mfp_a[bin].y) / delta_e;
-      t->mfp_b[bin].z = (t->mfp_a[bin + MCGPU_MAX_MATERIALS].z - t->mfp_a[bin].z) / delta_e;
-    }
-    t->mfp_b[(size_t)(n_values - 1) * MCGPU_MAX_MATERIALS + mat] = t->mfp_b[(size_t)(n_values - 2) * MCGPU_MAX_MATERIALS + mat];
-    for (i = 0; i < n_values; i++) {
-      const size_t bin = (size_t)i * MCGPU_MAX_MATERIALS + mat;
-      const double e = t->e0 + i * delta_e;
-      t->mfp_a[bin].x = t->mfp_a[bin].x - e * t->mfp_b[bin].x;
-      t->mfp_a[bin].y = t->mfp_a[bin].y - e * t->mfp_b[bin].y;
-      t->mfp_a[bin].z = t->mfp_a[bin].z - e * t->mfp_b[bin].z;
-    }
-
-    /* -- Rayleigh RITA grid (H:2361-2394) */
-    if (!seek_gz(f, "[DATA VALUES", line)) MBAIL("load_material: Rayleigh data not found in file '%s'", paths[mat]);
-    gzgets(f, line, MCGPU_LINE);
-    sscanf(line, "# %d", &n_rayleigh);
-    if (n_rayleigh != MCGPU_NP_RAYLEIGH) MBAIL("load_material: %d Rayleigh sampling values in '%s', expected %d", n_rayleigh, paths[mat], MCGPU_NP_RAYLEIGH);
-    gzgets(f, line, MCGPU_LINE);
-    for (i = 0; i < n_rayleigh; i++) {
-      const int bin = MCGPU_NP_RAYLEIGH * mat + i;
-      int itl = 0, itu = 0;
-      gzgets(f, line, MCGPU_LINE);
-      sscanf(line, "  %e  %e  %e  %e  %d  %d", &t->ray_xco[bin], &t->ray_pco[bin], &t->ray_aco[bin], &t->ray_bco[bin], &itl, &itu);
-      t->ray_itlco[bin] = (uint8_t)itl;
-      t->ray_ituco[bin] = (uint8_t)itu;
-    }
-
-    /* -- Compton shells (H:2398-2426) */
-    if (!seek_gz(f, "[NUMBER OF SHELLS", line)) MBAIL("load_material: Compton data not found in file '%s'", paths[mat]);
-    gzgets(f, line, MCGPU_LINE);
-    sscanf(line, "# %d", &n_shells);
-    if (n_shells > MCGPU_MAX_SHELLS || n_shells < 0) MBAIL("load_material: too many Compton shells in '%s': %d (max %d)", paths[mat], n_shells, MCGPU_MAX_SHELLS);
-    t->cmp_noscco[mat] = n_shells;
-    gzgets(f, line, MCGPU_LINE);
-    for (i = 0; i < n_shells; i++) {
-      const int bin = mat + i * MCGPU_MAX_MATERIALS;
-      int kz, ks;
-      gzgets(f, line, MCGPU_LINE);
-      sscanf(line, " %e  %e  %e  %d  %d", &t->cmp_fco[bin], &t->cmp_uico[bin], &t->cmp_fj0[bin], &kz, &ks);
-    }
-    gzclose(f);
-    t->material_loaded[mat] = 1;
-#undef MBAIL
   }
+  for (i = 0; i < n_jobs; i++) free(jobs[i].wood);
+  if (rc != MCGPU_OK) return rc;
 
   /* -- Woodcock majorant: slope and re-based intercept (H:2434-2441).  The reference leaves the
    *    last slope unassigned (Q3); it is defined here as the previous one, like mfp_b. */
