@@ -12,8 +12,10 @@
  *
  * Built with -DMCGPU_BATCH_MAIN the same file gives MC-GPU_v1.3_batch.x <a.in> <b.in> ...: the 4D case
  * (one input file per respiratory phase, cbctmc/mc/simulation.py:622-692) in ONE process, so that the CUDA
- * context and the device buffers are set up once instead of once per phase.  Every input
- * is simulated exactly as a separate invocation would (same seeds, same files). */
+ * context and the device buffers are set up once instead of once per phase, and the next input is
+ * parsed and uploaded (into a second context) while the current one is simulated.  Every input is simulated
+ * exactly as a separate invocation would (same seeds, same files). */
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -47,15 +49,19 @@ static int die(mcgpu_ctx* ctx, int rc) {
   return rc;
 }
 
-static int run_one(mcgpu_ctx* ctx, const char* in_path, const struct timespec* t0) {
-  struct timespec t1, t2;
-  mcgpu_info info;
-  double t_init, t_total;
+static int load_one(mcgpu_ctx* ctx, const char* in_path) {
   int rc;
   printf("\n    -- Reading the input file '%s':\n", in_path);
   if ((rc = mcgpu_load_input(ctx, in_path)) != MCGPU_OK) return rc;
   if ((rc = mcgpu_load_voxels(ctx, NULL)) != MCGPU_OK) return rc;
-  if ((rc = mcgpu_load_materials(ctx, NULL, 0)) != MCGPU_OK) return rc;
+  return mcgpu_load_materials(ctx, NULL, 0);
+}
+
+static int simulate_one(mcgpu_ctx* ctx, const struct timespec* t0) {
+  struct timespec t1, t2;
+  mcgpu_info info;
+  double t_init, t_total;
+  int rc;
   mcgpu_get_info(ctx, &info);
   printf("              x-ray tracks to simulate = %llu\n", info.requested_histories);
   printf("                   initial random seed = %d\n", info.seed_input);
@@ -91,11 +97,26 @@ static int run_one(mcgpu_ctx* ctx, const char* in_path, const struct timespec* t
   return MCGPU_OK;
 }
 
+#ifdef MCGPU_BATCH_MAIN
+/* the next input is parsed and uploaded by this thread, into the other context, while the current one is simulated */
+typedef struct {
+  mcgpu_ctx* ctx;
+  const char* path;
+  int rc;
+} prefetch_job;
+
+static void* prefetch_main(void* arg) {
+  prefetch_job* j = (prefetch_job*)arg;
+  j->rc = load_one(j->ctx, j->path);
+  return NULL;
+}
+#endif
+
 int main(int argc, char** argv) {
   struct timespec t0;
   mcgpu_ctx* ctx;
   time_t now = time(NULL);
-  int rc, k;
+  int rc;
 
   if (launcher_rank() != 0) return 0;
   clock_gettime(CLOCK_MONOTONIC, &t0);
@@ -122,10 +143,45 @@ int main(int argc, char** argv) {
     return -4;
   }
   mcgpu_set_verbose(ctx, 1);
-  for (k = 1; k < argc; k++) {
-    if (k > 1) clock_gettime(CLOCK_MONOTONIC, &t0);
-    if ((rc = run_one(ctx, argv[k], &t0)) != MCGPU_OK) return die(ctx, rc);
+#ifndef MCGPU_BATCH_MAIN
+  if ((rc = load_one(ctx, argv[1])) != MCGPU_OK) return die(ctx, rc);
+  if ((rc = simulate_one(ctx, &t0)) != MCGPU_OK) return die(ctx, rc);
+#else
+  {
+    mcgpu_ctx* both[2];
+    int k;
+    both[0] = ctx;
+    both[1] = argc > 2 ? mcgpu_create(NULL, 0) : NULL;
+    if (argc > 2 && !both[1]) {
+      printf("\n\n   !!out of memory creating the context!!\n\n");
+      mcgpu_destroy(ctx);
+      return -4;
+    }
+    if (both[1]) mcgpu_set_verbose(both[1], 1);
+    if ((rc = load_one(both[0], argv[1])) != MCGPU_OK) {
+      if (both[1]) mcgpu_destroy(both[1]);
+      return die(both[0], rc);
+    }
+    for (k = 1; k < argc; k++) {
+      mcgpu_ctx* cur = both[(k - 1) & 1];
+      prefetch_job job;
+      pthread_t th;
+      int have_thread = 0;
+      job.ctx = both[k & 1], job.path = k + 1 < argc ? argv[k + 1] : NULL, job.rc = MCGPU_OK;
+      if (job.path) have_thread = pthread_create(&th, NULL, prefetch_main, &job) == 0;
+      rc = simulate_one(cur, &t0);
+      if (job.path && !have_thread) job.rc = load_one(job.ctx, job.path); /* no thread: load in turn */
+      if (have_thread) pthread_join(th, NULL);
+      if (rc != MCGPU_OK || job.rc != MCGPU_OK) {
+        mcgpu_ctx* bad = rc != MCGPU_OK ? cur : job.ctx;
+        mcgpu_destroy(bad == both[0] ? both[1] : both[0]);
+        return die(bad, rc != MCGPU_OK ? rc : job.rc);
+      }
+      clock_gettime(CLOCK_MONOTONIC, &t0);
+    }
+    if (both[1]) mcgpu_destroy(both[1]);
   }
+#endif
   now = time(NULL);
   printf("\n****** Code execution finished on: %s\n\n", ctime(&now));
   mcgpu_destroy(ctx);

@@ -62,7 +62,7 @@ $(BINDIR)/MC-GPU_v1.3.x: $(HOSTDIR)/main.c $(LIBDIR)/libmcgpu_b200.so
 # several input files (the respiratory phases of a 4D scan) in one process: one CUDA context
 $(BINDIR)/MC-GPU_v1.3_batch.x: $(HOSTDIR)/main.c $(LIBDIR)/libmcgpu_b200.so
 	@mkdir -p $(BINDIR)
-	$(CC) $(CFLAGS) -DMCGPU_BATCH_MAIN -fPIE $< -o $@ -L$(LIBDIR) -lmcgpu_b200 -Wl,-rpath,'$$ORIGIN/../lib'
+	$(CC) $(CFLAGS) -DMCGPU_BATCH_MAIN -fPIE $< -o $@ -L$(LIBDIR) -lmcgpu_b200 -lpthread -Wl,-rpath,'$$ORIGIN/../lib'
 
 clean:
 	rm -rf $(BUILD) $(LIBDIR) $(BINDIR)
