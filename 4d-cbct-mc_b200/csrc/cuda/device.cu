@@ -153,6 +153,11 @@ extern "C" int mcgpu_dev_upload(struct mcgpu_device* d, const mcgpu_scene* s, co
 }
 
 extern "C" int mcgpu_dev_launch(struct mcgpu_device* d, const mcgpu_view* view, const mcgpu_launch* l, char* err, size_t errlen) {
+  if ((size_t)4 * (size_t)view->total_num_pixels != d->image_words) {  // a pose of another detector would tally past the end of d_image
+    snprintf(err, errlen, "device %d: the projection has %d pixels but the uploaded image holds %zu; load the materials again after a new input", d->ordinal,
+             view->total_num_pixels, d->image_words / 4);
+    return -1;
+  }
   return d->fast_math ? mcgpu_launch_fast(d, view, l, err, errlen) : mcgpu_launch_exact(d, view, l, err, errlen);
 }
 

@@ -68,6 +68,9 @@ int mcgpu_load_input(mcgpu_ctx* ctx, const char* in_path) {
   free(ctx->views);
   ctx->views = NULL;
   ctx->have_input = 0;
+  /* the devices hold the previous input's spectrum and an image sized for its detector: a new input needs
+   * mcgpu_load_materials again (which re-uploads everything) before anything can run */
+  ctx->have_tables = 0;
   if ((rc = mcgpu_parse_input(ctx, in_path)) != MCGPU_OK) return rc;
   if ((rc = mcgpu_read_spectrum(ctx, ctx->in.file_espc)) != MCGPU_OK) return rc;
   if ((rc = mcgpu_build_views(ctx)) != MCGPU_OK) return rc;
@@ -233,7 +236,7 @@ typedef struct scan_shared {
 
 typedef struct scan_worker {
   scan_shared* sh;
-  int device;
+  int device, started;
   char err[512];
 } scan_worker;
 
@@ -377,7 +380,11 @@ int mcgpu_run_all(mcgpu_ctx* ctx, mcgpu_progress_cb cb, void* user) {
     for (d = 0; d < n; d++) {
       workers[d].sh = &sh;
       workers[d].device = d;
-      pthread_create(&threads[d], NULL, scan_thread, &workers[d]);
+      workers[d].started = pthread_create(&threads[d], NULL, scan_thread, &workers[d]) == 0;
+      if (!workers[d].started) { /* e.g. the container's thread limit: fail this device's projections instead of waiting for them forever */
+        snprintf(workers[d].err, sizeof workers[d].err, "run_all: cannot start the host thread of device %d", d);
+        for (p = d; p < P; p += n) scan_publish(&sh, p, MCGPU_E_NOMEM, 0.0);
+      }
     }
     rc = MCGPU_OK;
     for (p = 0; p < P && rc == MCGPU_OK; p++) {
@@ -402,7 +409,8 @@ int mcgpu_run_all(mcgpu_ctx* ctx, mcgpu_progress_cb cb, void* user) {
           if (sh.done[q] < 0) rc = sh.done[q];
       }
     }
-    for (d = 0; d < n; d++) pthread_join(threads[d], NULL);
+    for (d = 0; d < n; d++)
+      if (workers[d].started) pthread_join(threads[d], NULL);
     ctx->verbose = verbose;
     if (rc != MCGPU_OK)
       for (d = 0; d < n; d++)

@@ -24,7 +24,8 @@
 #include "mcgpu_b200.h"
 
 static int launcher_rank(void) {
-  const char* names[] = {"OMPI_COMM_WORLD_RANK", "PMI_RANK", "PMIX_RANK", "MV2_COMM_WORLD_RANK", "SLURM_PROCID"};
+  /* MPI launchers only: SLURM_PROCID alone (srun -n4 ... phase_$SLURM_PROCID.in) is one independent run per task */
+  const char* names[] = {"OMPI_COMM_WORLD_RANK", "PMI_RANK", "PMIX_RANK", "MV2_COMM_WORLD_RANK"};
   size_t i;
   for (i = 0; i < sizeof names / sizeof names[0]; i++) {
     const char* v = getenv(names[i]);
@@ -49,9 +50,9 @@ static int die(mcgpu_ctx* ctx, int rc) {
   return rc;
 }
 
-static int load_one(mcgpu_ctx* ctx, const char* in_path) {
+static int load_one(mcgpu_ctx* ctx, const char* in_path, int quiet) {
   int rc;
-  printf("\n    -- Reading the input file '%s':\n", in_path);
+  if (!quiet) printf("\n    -- Reading the input file '%s':\n", in_path);
   if ((rc = mcgpu_load_input(ctx, in_path)) != MCGPU_OK) return rc;
   if ((rc = mcgpu_load_voxels(ctx, NULL)) != MCGPU_OK) return rc;
   return mcgpu_load_materials(ctx, NULL, 0);
@@ -107,7 +108,10 @@ typedef struct {
 
 static void* prefetch_main(void* arg) {
   prefetch_job* j = (prefetch_job*)arg;
-  j->rc = load_one(j->ctx, j->path);
+  /* silent: cbctmc scrapes stdout of the RUNNING scan for its progress bar; this context's banners would land in the middle */
+  mcgpu_set_verbose(j->ctx, 0);
+  j->rc = load_one(j->ctx, j->path, 1);
+  mcgpu_set_verbose(j->ctx, 1);
   return NULL;
 }
 #endif
@@ -118,7 +122,10 @@ int main(int argc, char** argv) {
   time_t now = time(NULL);
   int rc;
 
-  if (launcher_rank() != 0) return 0;
+  if (launcher_rank() != 0) {
+    printf("MC-GPU (mcgpu-b200): MPI rank %d has nothing to do -- rank 0 drives every visible GPU in one process; exiting.\n", launcher_rank());
+    return 0;
+  }
   clock_gettime(CLOCK_MONOTONIC, &t0);
 #ifdef MCGPU_BATCH_MAIN
   if (argc < 2) {
@@ -144,7 +151,7 @@ int main(int argc, char** argv) {
   }
   mcgpu_set_verbose(ctx, 1);
 #ifndef MCGPU_BATCH_MAIN
-  if ((rc = load_one(ctx, argv[1])) != MCGPU_OK) return die(ctx, rc);
+  if ((rc = load_one(ctx, argv[1], 0)) != MCGPU_OK) return die(ctx, rc);
   if ((rc = simulate_one(ctx, &t0)) != MCGPU_OK) return die(ctx, rc);
 #else
   {
@@ -158,7 +165,7 @@ int main(int argc, char** argv) {
       return -4;
     }
     if (both[1]) mcgpu_set_verbose(both[1], 1);
-    if ((rc = load_one(both[0], argv[1])) != MCGPU_OK) {
+    if ((rc = load_one(both[0], argv[1], 0)) != MCGPU_OK) {
       if (both[1]) mcgpu_destroy(both[1]);
       return die(both[0], rc);
     }
@@ -170,8 +177,11 @@ int main(int argc, char** argv) {
       job.ctx = both[k & 1], job.path = k + 1 < argc ? argv[k + 1] : NULL, job.rc = MCGPU_OK;
       if (job.path) have_thread = pthread_create(&th, NULL, prefetch_main, &job) == 0;
       rc = simulate_one(cur, &t0);
-      if (job.path && !have_thread) job.rc = load_one(job.ctx, job.path); /* no thread: load in turn */
-      if (have_thread) pthread_join(th, NULL);
+      if (job.path && !have_thread) job.rc = load_one(job.ctx, job.path, 0); /* no thread: load in turn */
+      if (have_thread) {
+        pthread_join(th, NULL);
+        if (job.rc == MCGPU_OK) printf("\n    -- Input file '%s' was read while the previous one was simulated.\n", job.path);
+      }
       if (rc != MCGPU_OK || job.rc != MCGPU_OK) {
         mcgpu_ctx* bad = rc != MCGPU_OK ? cur : job.ctx;
         mcgpu_destroy(bad == both[0] ? both[1] : both[0]);

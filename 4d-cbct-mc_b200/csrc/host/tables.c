@@ -160,6 +160,8 @@ static void load_one_material(material_job* j) {
   }
 
   gzgets(f, line, MCGPU_LINE);
+  if (strstr(line, "#[STUB")) /* header-only file (an asset staged without its rows) for a material the voxels DO use */
+    MFAIL(MCGPU_E_PARSE, "load_material: '%s' is a header-only stub (no cross-section rows) but material %d is present in the voxels; stage the full .mcgpu file", j->path, mat + 1);
   gzgets(f, line, MCGPU_LINE);
   sscanf(line, "# %d", &n_values);
   if (mat == 0) {

@@ -32,6 +32,8 @@ static int alloc_volume(mcgpu_ctx* ctx, int nx, int ny, int nz, const float* siz
   mcgpu_volume* v = &ctx->vol;
   size_t n;
   int k;
+  ctx->have_voxels = 0; /* a failed (re)load must not leave a context that still looks runnable with vol.* == NULL */
+  ctx->have_tables = 0;
   mcgpu_free_volume(v);
   if (nx < 1 || ny < 1 || nz < 1 || (double)nx * ny * nz > 2147483647.0)
     return mcgpu_fail(ctx, MCGPU_E_PARSE, "load_voxels: invalid number of voxels %d x %d x %d", nx, ny, nz);
@@ -288,7 +290,14 @@ int mcgpu_read_voxels(mcgpu_ctx* ctx, const char* path) {
   pthread_mutex_init(&pool.mu, NULL);
   pthread_cond_init(&pool.cv_work, NULL);
   pthread_cond_init(&pool.cv_done, NULL);
-  for (i = 0; i < n_threads; i++) pthread_create(&threads[i], NULL, vox_worker, &pool);
+  { /* only threads that really started are waited for and joined; with none the blocks are parsed inline */
+    int created = 0;
+    for (i = 0; i < n_threads; i++) {
+      if (pthread_create(&threads[created], NULL, vox_worker, &pool) != 0) break;
+      created++;
+    }
+    n_threads = created;
+  }
   carry_buf = (char*)malloc(VOX_BLOCK + 1);
 
   while (rc == MCGPU_OK && (filled < n) && (!eof || r_count > 0)) {
@@ -353,6 +362,11 @@ int mcgpu_read_voxels(mcgpu_ctx* ctx, const char* path) {
       }
       ring[(r_head + r_count) % RING] = t;
       r_count++;
+      if (n_threads == 0) { /* no worker could be created (thread limit of the container): parse here */
+        vox_parse(t);
+        t->done = 1;
+        continue;
+      }
       pthread_mutex_lock(&pool.mu);
       if (pool.tail)
         pool.tail->next = t;

@@ -156,3 +156,50 @@ def line_pairs(shape=(305, 300, 152), spacing_mm=(1.0, 1.0, 1.0), upsample_x: in
         pos += 2.0
     _paint(mats, dens, insert & bars[:, None, None], "aluminium")
     return Phantom(f"line_pairs_{fine[0]}x{fine[1]}x{fine[2]}", mats, dens, (sx / 10, spacing_mm[1] / 10, spacing_mm[2] / 10))
+
+
+def patient(shape=(256, 256, 100), spacing_mm: float = 2.0) -> Phantom:
+    """Patient-like trunk in cbctmc's PATIENT material set (cbctmc/mc/geometry.py:130-229: bone mapper with red
+    marrow, lung vessels = blood, liver, stomach/intestines, muscle, fat) -- the tissues whose Compton profiles have the
+    most shells (blood 40 = MAX_SHELLS, red marrow 36): adipose rim, muscle layer, soft-tissue interior, lungs with
+    blood vessels, liver and stomach below the diaphragm, vertebra and ribs of bone_020/050/100 around red marrow,
+    cartilage discs and a gland."""
+    mats, dens = _blank(shape)
+    x, y, z = _grid(shape)
+    s = spacing_mm
+    cx, cy, nz = shape[0] / 2, shape[1] / 2, shape[2]
+    allz = z >= 0
+
+    def ell(ax_mm, ay_mm, ox_mm=0.0, oy_mm=0.0):
+        return ((x - cx - ox_mm / s) / (ax_mm / s)) ** 2 + ((y - cy - oy_mm / s) / (ay_mm / s)) ** 2 <= 1.0
+
+    _paint(mats, dens, ell(170, 120) & allz, "adipose")
+    _paint(mats, dens, ell(158, 108) & allz, "muscle_tissue")
+    _paint(mats, dens, ell(146, 96) & allz, "soft_tissue")
+    z_dia = 0.45 * nz  # diaphragm: abdomen organs below, lungs above
+    upper, lower = z >= z_dia, z < z_dia
+    for sgn in (-1, 1):
+        lung = ell(52, 74, sgn * 74.0, -6.0) & upper
+        _paint(mats, dens, lung, "lung", density=0.26)
+        # vessel tree: blood cylinders along z and a few oblique branches
+        for k, (ox, oy, r) in enumerate([(60, -20, 5.0), (85, 10, 3.5), (70, 25, 3.0), (95, -30, 2.5)]):
+            tilt = 0.15 * (k - 1.5)
+            vessel = ((x - cx - sgn * ox / s - tilt * (z - z_dia)) ** 2 + (y - cy - oy / s) ** 2 <= (r / s) ** 2) & upper
+            _paint(mats, dens, vessel & lung, "blood")
+    _paint(mats, dens, ell(28, 32, 10.0, -10.0) & upper, "blood")  # heart / great vessels
+    _paint(mats, dens, ell(70, 60, -55.0, -10.0) & lower, "liver")
+    _paint(mats, dens, ell(45, 40, 65.0, -15.0) & lower, "stomach_intestines")
+    _paint(mats, dens, ell(12, 10, 60.0, 40.0) & lower, "glands_others")
+    # ribs: shell of cortical bone around red marrow, alternating z bands
+    band = (np.floor(z * s / 12.0) % 2) == 0
+    _paint(mats, dens, ell(144, 94) & ~ell(132, 82) & band, "bone_100")
+    _paint(mats, dens, ell(140, 90) & ~ell(136, 86) & band, "red_marrow")
+    # vertebral column: bone_100 shell, bone_050 / bone_020 spongiosa, red marrow core, cartilage discs
+    disc = (np.floor(z * s / 30.0) % 2) == 1
+    sp = lambda r: ((x - cx) ** 2 + (y - cy - 62.0 / s) ** 2 <= (r / s) ** 2) & allz  # noqa: E731
+    _paint(mats, dens, sp(20), "bone_100")
+    _paint(mats, dens, sp(17), "bone_050")
+    _paint(mats, dens, sp(13), "bone_020")
+    _paint(mats, dens, sp(8), "red_marrow")
+    _paint(mats, dens, sp(20) & disc & (np.floor(z * s / 6.0) % 5 == 0), "cartilage")
+    return Phantom(f"patient_{shape[0]}x{shape[1]}x{shape[2]}", mats, dens, (spacing_mm / 10,) * 3)

@@ -50,6 +50,9 @@ CASES = {
     "thorax_oblique": (("thorax", dict(shape=(32, 32, 12), spacing_mm=16.0)),
                        dict(n_histories=100_000, n_detector_pixels=(66, 28), polar_aperture=(10.0, 5.0), azimuthal_aperture=8.0,
                             n_projections=2, angle_between_projections=45.0, source_direction=(1.0, 1.0, 0.0), sad=300.0)),
+    # cbctmc's patient material set: blood (40 Compton shells = MAX_SHELLS), red marrow (36), muscle, liver, stomach, glands, cartilage
+    "patient_p2": (("patient", dict(shape=(64, 64, 25), spacing_mm=8.0)),
+                   dict(n_histories=120_000, n_detector_pixels=(66, 28), n_projections=2, angle_between_projections=135.0)),
 }
 
 

@@ -31,7 +31,10 @@ from conftest import CASES, build_case  # noqa: E402
 
 def main():
     assert oracle_py.REF_CPU.exists(), "run `make -C oracle ref` first"
+    only = sys.argv[1:]  # optional: regenerate just these cases
     for name in CASES:
+        if only and name not in only:
+            continue
         with tempfile.TemporaryDirectory() as tmp:
             tmp = Path(tmp)
             inp, cfg, _ = build_case(pkg, name, tmp)

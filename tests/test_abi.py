@@ -94,13 +94,20 @@ def test_executable_fails_without_gpu_and_with_bad_args(pkg, cases):
 
 
 def test_executable_tolerates_mpirun_style_launch(pkg, cases):
-    """`mpirun -n N MC-GPU_v1.3.x input.in` starts N copies; ranks > 0 must exit 0 silently."""
+    """`mpirun -n N MC-GPU_v1.3.x input.in` starts N copies; ranks > 0 must exit 0 with a one-line notice (nothing cbctmc's
+    stdout scraping reacts to: no "error", no "Simulating Projection").  SLURM_PROCID alone is NOT an MPI launch
+    (`srun -n4 MC-GPU_v1.3.x phase_$SLURM_PROCID.in` = independent runs), so it must not silence a process."""
     import os
 
     exe = ROOT / "4d-cbct-mc_b200" / "bin" / "MC-GPU_v1.3.x"
-    env = dict(os.environ, OMPI_COMM_WORLD_RANK="1")
+    for var in ("OMPI_COMM_WORLD_RANK", "PMI_RANK", "PMIX_RANK", "MV2_COMM_WORLD_RANK"):
+        env = dict(os.environ, **{var: "1"})
+        res = subprocess.run([str(exe), str(cases["water_p1"][0])], capture_output=True, text=True, env=env)
+        assert res.returncode == 0 and len(res.stdout.strip().splitlines()) == 1 and "rank 1 has nothing to do" in res.stdout
+        assert "error" not in res.stdout.lower() and "Simulating Projection" not in res.stdout
+    env = dict(os.environ, SLURM_PROCID="3")
     res = subprocess.run([str(exe), str(cases["water_p1"][0])], capture_output=True, text=True, env=env)
-    assert res.returncode == 0 and res.stdout == ""
+    assert "Reading the input file" in res.stdout  # it runs (and, without a GPU, fails loudly later)
 
 
 def test_time_limited_mode_is_rejected(pkg, cases, tmp_path):
@@ -112,3 +119,26 @@ def test_time_limited_mode_is_rejected(pkg, cases, tmp_path):
         with pytest.raises(pkg.engine.McgpuError) as e:
             eng.load_input(f)
         assert e.value.code == -2 and "seconds" in str(e.value)
+
+
+def test_a_new_input_or_a_failed_voxel_load_invalidates_what_the_devices_hold(pkg, cases, tmp_path):
+    """The devices keep the spectrum and an image sized for the detector of the input they were uploaded with: after
+    mcgpu_load_input the context must ask for load_materials again instead of running with stale device state, and a
+    failed load_voxels must not leave a context that still looks runnable."""
+    with pkg.engine.Engine() as eng:
+        eng.load_input(cases["water_p1"][0]).load_voxels().load_materials()
+        eng.load_input(cases["thorax_p4"][0])
+        with pytest.raises(pkg.engine.McgpuError) as e:
+            eng.run_projection(0)
+        assert e.value.code == -6  # MCGPU_E_STATE, before the "no device" check
+        eng.load_voxels().load_materials()
+        bad = tmp_path / "truncated.vox"  # valid header, then the data ends: fails AFTER the old volume was released
+        bad.write_text("[SECTION VOXELS HEADER v.2008-04-13]\n4 4 4\n1.0 1.0 1.0\n1\n2\n1\n[END OF VXH SECTION]\n1 1.0\n1 1.0\n")
+        with pytest.raises(pkg.engine.McgpuError):
+            eng.load_voxels(bad)
+        assert eng.info.num_voxels_x == 0
+        with pytest.raises(pkg.engine.McgpuError) as e:
+            eng.run_projection(0)
+        assert e.value.code == -6
+        with pytest.raises(pkg.engine.McgpuError):  # an error, not a NULL dereference, in the dose path either
+            eng.dose("voxels")

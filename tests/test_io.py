@@ -223,3 +223,47 @@ def test_binary_geometry_gives_the_same_volume_as_the_text_file(pkg, cases, tmp_
             eng.load_voxels(tmp_path / "short.voxb")
         with pytest.raises(pkg.engine.McgpuError, match="out of range"):
             eng.load_voxels(tmp_path / "bad.voxb")
+
+
+def test_header_only_material_stub_is_named_as_such(pkg, cases, tmp_path):
+    """A material file cut after its nominal density (an asset staged without rows) is fine for a material the voxels do
+    not use (H:2220-2233 reads only the header) but must be reported as a stub -- not as 'incorrect number of energy
+    values: input=0' -- when the voxels use it."""
+    import gzip
+    import re
+
+    inp, _, _ = cases["thorax_p4"]
+    paths = list(pkg.mcio.material_paths())
+    numbers = pkg.mcio.material_numbers()
+
+    def stub_of(ident):
+        src = paths[numbers[ident] - 1]
+        payload = gzip.open(src, "rb").read()
+        m = re.search(rb"\[NOMINAL DENSITY[^\n]*\n[^\n]*\n", payload)
+        dst = tmp_path / f"{ident}_stub.mcgpu.gz"
+        with gzip.open(dst, "wb") as f:
+            f.write(payload[: m.end()] + b"#[STUB: rows omitted]\n")
+        return dst
+
+    with load(pkg, inp) as eng:
+        eng.load_voxels()
+        unused = list(paths)
+        unused[numbers["teflon"] - 1] = stub_of("teflon")  # not in the thorax phantom
+        eng.load_materials(unused)
+        used = list(paths)
+        used[numbers["lung"] - 1] = stub_of("lung")
+        with pytest.raises(pkg.engine.McgpuError) as e:
+            eng.load_materials(used)
+        assert e.value.code == -2 and "header-only stub" in str(e.value) and "lung" in str(e.value)
+
+
+def test_every_material_of_the_patient_set_ships_in_full(pkg):
+    """cbctmc's patient geometries use blood (40 shells = MAX_SHELLS), red_marrow (36), liver, muscle, stomach, glands,
+    cartilage (cbctmc/mc/geometry.py:161, 214-229): all 22 files carry their tables."""
+    import gzip
+
+    rows = pkg.mcio.material_table()
+    assert len(rows) == 22
+    for _, ident, _, path in rows:
+        text = gzip.open(path, "rt").read()
+        assert "STUB" not in text and text.count("\n") > 20000, ident

@@ -16,8 +16,11 @@ ROOT = Path(__file__).resolve().parents[1]
 
 def line_map(kernel_sub):
     tmp = tempfile.mkdtemp()
-    subprocess.run(["cuobjdump", "-xelf", "all", str(ROOT / "4d-cbct-mc_b200/lib/libmcgpu_b200.so")], cwd=tmp, check=True, capture_output=True)
-    txt = subprocess.run(["nvdisasm", "-g", "-c", str(Path(tmp) / "device.sm_100a.cubin")], capture_output=True, text=True).stdout
+    # the library holds two cubins of the same name (exact / fast-math build of launch.cu): take the object file of the build asked for
+    obj = ROOT / "build" / ("launch_fast.o" if "mcgpu_fast" in kernel_sub else "launch_exact.o")
+    subprocess.run(["cuobjdump", "-xelf", "all", str(obj)], cwd=tmp, check=True, capture_output=True)
+    cubin = next(Path(tmp).glob("*.cubin"))
+    txt = subprocess.run(["nvdisasm", "-g", "-c", str(cubin)], capture_output=True, text=True).stdout
     lines = txt.splitlines()
     start = next(i for i, l in enumerate(lines) if l.startswith("\t.section\t.text.") and kernel_sub in l)
     out, cur = [], ("?", 0)

@@ -10,8 +10,9 @@ material order = density-sorted list, cbctmc/mc/materials.py:112-119).
 workloads need are gzip'ed (byte-exact payload, mtime=0 so the output is
 reproducible) into assets/materials/.  MC-GPU reads .gz material files through
 zlib (MC-GPU_v1.3.cu:2199), and it only reads the *header* of materials that
-do not appear in the voxel file (MC-GPU_v1.3.cu:2220-2233), so for materials no
-synthetic phantom uses a header-only stub is written instead of 3.6 MB of rows.
+do not appear in the voxel file (MC-GPU_v1.3.cu:2220-2233).  ALL 22 files are staged in full:
+cbctmc's patient geometries use blood (40 shells = MAX_SHELLS), red_marrow (36), muscle, liver,
+stomach/intestines, glands and cartilage (cbctmc/mc/geometry.py:161, 214-229).
 
 Run once in the build container:  python tools/stage_assets.py
 """
@@ -26,11 +27,6 @@ REF = Path(os.environ.get("MCGPU_REFERENCE", "/root/reference")) / "cbctmc" / "a
 ROOT = Path(__file__).resolve().parents[1]
 OUT = ROOT / "assets"
 
-# materials that at least one synthetic workload (phantoms.py) puts in voxels
-FULL = {
-    "air", "lung", "pmp", "ldpe", "adipose", "h2o", "soft_tissue", "polystyrene",
-    "bone_020", "acrylic", "bone_050", "delrin", "bone_100", "teflon", "aluminium",
-}
 SPECTRA = ["125kVp_0.89mmTi_varian_norm.spc"]
 
 
@@ -54,7 +50,7 @@ def main() -> int:
         for number, path in enumerate(order, start=1):
             ident = path.name.split("__")[0]
             rho = nominal_density(path)
-            full = ident in FULL
+            full = True
             order_f.write(f"{number} {ident} {rho:g} {'full' if full else 'stub'}\n")
             dst = OUT / "materials" / (path.name + ".gz")
             with open(path, "rb") as src:
