@@ -35,6 +35,18 @@ extern "C" struct mcgpu_device* mcgpu_dev_open(int ordinal, char* err, size_t er
   if (!d) return NULL;
   d->ordinal = ordinal;
   d->sm_count = prop.multiProcessorCount;
+  {  // tuning / A-B switches, read ONCE per device handle; the defaults are the product path.  The arithmetic mode
+     // is not among them: only mcgpu_set_fast_math selects it, so mcgpu_get_info always reports what runs.
+    const char* k = getenv("MCGPU_KERNEL");
+    const char* t = getenv("MCGPU_W_THRESHOLD");
+    d->kernel_generation = (k && atoi(k) == 1) ? 1 : (k && atoi(k) == 2) ? 2 : 3;
+    d->w_threshold = t ? atoi(t) : (d->kernel_generation == 3 ? 12 : 8);
+    d->wf_rows = getenv("MCGPU_WF_ROWS") ? atoi(getenv("MCGPU_WF_ROWS")) : 0;
+    if (d->wf_rows != 16 && d->wf_rows != 32) d->wf_rows = 0;
+    d->wf_block = (getenv("MCGPU_WF_BLOCK") && atoi(getenv("MCGPU_WF_BLOCK")) == 1024) ? 1024 : 512;
+    if (d->w_threshold < 1) d->w_threshold = 1;
+    if (d->w_threshold > 32) d->w_threshold = 32;
+  }
   if (cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&d->ev0) != cudaSuccess || cudaEventCreate(&d->ev1) != cudaSuccess) {
     snprintf(err, errlen, "cannot create stream/events on device %d: %s", ordinal, cudaGetErrorString(cudaGetLastError()));
     free(d);
@@ -106,19 +118,6 @@ extern "C" int mcgpu_dev_upload(struct mcgpu_device* d, const mcgpu_scene* s, co
     CK(cudaMalloc((void**)&d->d_voxels_edep, sizeof(unsigned long long) * 2 * (size_t)s->dose_roi_voxels));
     CK(cudaMemset(d->d_voxels_edep, 0, sizeof(unsigned long long) * 2 * (size_t)s->dose_roi_voxels));
   }
-  {  // tuning / A-B switches (documented in DESIGN.md); the defaults are the product path
-    const char* k = getenv("MCGPU_KERNEL");
-    const char* t = getenv("MCGPU_W_THRESHOLD");
-    d->kernel_generation = (k && atoi(k) == 1) ? 1 : (k && atoi(k) == 2) ? 2 : 3;
-    if (getenv("MCGPU_FAST_MATH")) d->fast_math = atoi(getenv("MCGPU_FAST_MATH")) != 0;  // A/B convenience; the API is mcgpu_set_fast_math
-    d->w_threshold = t ? atoi(t) : (d->kernel_generation == 3 ? 12 : 8);
-    d->wf_rows = getenv("MCGPU_WF_ROWS") ? atoi(getenv("MCGPU_WF_ROWS")) : 0;
-    if (d->wf_rows != 16 && d->wf_rows != 32) d->wf_rows = 0;
-    d->wf_block = (getenv("MCGPU_WF_BLOCK") && atoi(getenv("MCGPU_WF_BLOCK")) == 1024) ? 1024 : 512;
-    if (d->w_threshold < 1) d->w_threshold = 1;
-    if (d->w_threshold > 32) d->w_threshold = 32;
-  }
-
   McgpuSceneDev& sc = d->scene;
   memset(&sc, 0, sizeof sc);
   sc.volume = d->d_volume;

@@ -7,8 +7,11 @@
 #include <string.h>
 
 #include "transport.cuh"
-#include "regroup.cuh"
 #include "wavefront.cuh"
+#ifdef MCGPU_AB_KERNELS  // generations 1 and 2, for A/B measurements only (make AB=1)
+#include "regroup.cuh"
+#include "streams.cuh"
+#endif
 
 #define CK(call)                                                                                    \
   do {                                                                                              \

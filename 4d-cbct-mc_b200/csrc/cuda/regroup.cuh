@@ -1,4 +1,5 @@
 // Transport kernel, generation 2: persistent warps that regroup photons by event.
+// A/B ONLY: compiled when the library is built with `make AB=1` (-DMCGPU_AB_KERNELS); the product is wavefront.cuh.
 //
 // Why: the reference's structure (one thread = one stream, nested variable-length loops:
 // histories > interactions > delta-tracking steps, rejection loops over up to 34 shells inside
@@ -35,13 +36,52 @@
 #endif
 namespace MCGPU_NS {
 
-enum LaneState : int { ST_W = 0, ST_C = 1, ST_CT = 2, ST_R = 3, ST_T = 4, ST_N = 5, ST_I = 6, ST_F = 7 };
-
-#define MCGPU_FULL_MASK 0xffffffffu
 #define MCGPU_REGROUP_BLOCK 128
 
-__host__ __device__ inline int regroup_scratch_stride(int max_shells) { return max_shells | 1; }  // odd: conflict-free rows
 #define MCGPU_SCRATCH_ROWS 16  // photons per cooperative Compton call; further lanes wait for the next event phase
+
+// Warp-cooperative evaluation of the shell terms of every photon whose lane is in `mask`: the
+// (photon, shell) pairs are spread over all 32 lanes (G lanes per photon, G the largest power of
+// two with G*popc(mask) <= 32), results go to the warp's scratch row of the photon's rank.  The
+// owner lane then adds fco*term in shell order, exactly like the sequential loop of the reference,
+// so the sum is bit-identical while the expensive part (rsqrtf, expf) runs on full warps.
+__device__ __forceinline__ void coop_shell_terms(unsigned mask, float E, int slot, float factor, bool trial, const float4* __restrict__ sh_shells, const SceneDev& sc,
+                                                 float* __restrict__ wbuf, int stride, unsigned lane) {
+  const int n = __popc(mask);
+  int G = 32;
+  while (G * n > 32) G >>= 1;
+  const int g = (int)lane / G, sub = (int)lane % G;
+  const bool helper = g < n;
+  const int owner = helper ? (int)__fns(mask, 0, g + 1) : 0;
+  const float oE = __shfl_sync(0xffffffffu, E, owner);
+  const int oslot = __shfl_sync(0xffffffffu, slot, owner);
+  const float ofac = __shfl_sync(0xffffffffu, factor, owner);
+  const bool otrial = __shfl_sync(0xffffffffu, (int)trial, owner) != 0;
+  if (helper) {
+    const int nosc = sc.cmp_noscco[oslot];
+    const float4* sh = sh_shells + oslot * MCGPU_MAX_SHELLS;
+#pragma unroll 1
+    for (int i = sub; i < nosc; i += G) {
+      const float4 s4 = sh[i];
+      wbuf[g * stride + i] = s4.x * compton_shell_term(s4, oE, ofac, otrial);
+    }
+  }
+  __syncwarp();
+}
+
+// Ordered sum over the shells (the `s0 +=` / `s +=` chain of K:1337, K:1399) of the weighted terms the
+// helpers left in `row`.  With KEEP the running sums replace the terms: they are the reference's
+// `pac` values of the target-shell search (K:1414-1422), which adds the same numbers in the same order.
+template <bool KEEP>
+__device__ __forceinline__ float compton_ordered_sum(int nosc, float* __restrict__ row) {
+  float s = 0.0f;
+#pragma unroll 1
+  for (int i = 0; i < nosc; i++) {
+    s += row[i];
+    if (KEEP) row[i] = s;
+  }
+  return s;
+}
 
 // keep the lowest MCGPU_SCRATCH_ROWS set bits of a lane mask
 __device__ __forceinline__ unsigned limit_rows(unsigned m) {

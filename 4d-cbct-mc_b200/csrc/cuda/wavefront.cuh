@@ -29,7 +29,7 @@
 // of batch, ONE cooperative shell-term call site for S0 and S(tau), rolled loops.  Measure
 // sm__icc_request_hit_rate / gcc__cache_requests_type_instruction (tools/icc_probe.sh) after any change.
 #pragma once
-#include "regroup.cuh"
+#include "transport.cuh"
 
 namespace MCGPU_NS {
 

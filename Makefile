@@ -19,7 +19,11 @@ NVFLAGS  := -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a \
 HOST_SRC := input.c geometry.c voxels.c tables.c ranecu_host.c report.c dose.c api.c post.c
 HOST_OBJ := $(HOST_SRC:%.c=$(BUILD)/%.o)
 CUDA_OBJ := $(BUILD)/device.o $(BUILD)/postprocess.o $(BUILD)/launch_exact.o $(BUILD)/launch_fast.o
-CUDA_HDR := $(CUDADIR)/transport.cuh $(CUDADIR)/regroup.cuh $(CUDADIR)/wavefront.cuh $(CUDADIR)/scene_dev.h $(CUDADIR)/device_internal.h $(HOSTDIR)/mcgpu_host.h
+CUDA_HDR := $(CUDADIR)/transport.cuh $(CUDADIR)/regroup.cuh $(CUDADIR)/streams.cuh $(CUDADIR)/wavefront.cuh $(CUDADIR)/scene_dev.h $(CUDADIR)/device_internal.h $(HOSTDIR)/mcgpu_host.h
+# AB=1 also compiles the two earlier kernel generations (MCGPU_KERNEL=1|2) for A/B measurements; the shipped library carries only the product kernel
+ifeq ($(AB),1)
+NVFLAGS += -DMCGPU_AB_KERNELS
+endif
 
 all: lib exe oracle
 

@@ -79,8 +79,14 @@ def test_every_kernel_generation_gives_the_same_tallies(pkg, gpu_engine_factory,
         eng.close()
     monkeypatch.setenv("MCGPU_KERNEL", generation)
     eng = gpu_engine_factory(inp)
-    assert np.array_equal(eng.run_projection(p), base), f"generation {generation}"
-    eng.close()
+    try:
+        other = eng.run_projection(p)
+    except pkg.engine.McgpuError as e:  # the shipped library carries only the product kernel; `make AB=1` adds generations 1 and 2
+        assert "not built with" in str(e)
+        pytest.skip("A/B kernel generations are not in this build (make AB=1)")
+    finally:
+        eng.close()
+    assert np.array_equal(other, base), f"generation {generation}"
 
 
 @pytest.mark.parametrize("name", ["water_p1", "thorax_p4", "air"])
