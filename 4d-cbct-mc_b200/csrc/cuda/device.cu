@@ -5,10 +5,32 @@
 #include "device_internal.h"
 
 
-// dst[i] += src[i]; src may live on a peer GPU (NVLink load) -- integer sums commute, so the
-// result is independent of how the streams were split.
-__global__ void accumulate_u64(unsigned long long* __restrict__ dst, const unsigned long long* __restrict__ src, size_t n) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] += src[i];
+// History-split reduction (the reference's MPI_Reduce of the partial images, MC-GPU_v1.3.cu:1019): the u64 tallies of the
+// devices that shared one projection's streams are summed on the first device.  Integer sums commute, so the result
+// does not depend on how the streams were split.  Two implementations behind mcgpu_dev_reduce:
+//   * ncclReduce(ncclUint64, ncclSum) over NVLink/NVSwitch with one communicator per device (ncclCommInitAll), all
+//     ranks driven from this process inside one ncclGroup -- the default when libnccl can be loaded;
+//   * accumulate_peers_u64: ONE kernel on the first device that reads every peer's image through NVLink peer
+//     mappings and adds them in a single pass over the destination (instead of n-1 passes) -- when NCCL is not
+//     available or MCGPU_REDUCE=peer.
+#define MCGPU_MAX_PEERS 16
+struct PeerImages {
+  const unsigned long long* src[MCGPU_MAX_PEERS];
+  int n;
+};
+
+__global__ void __launch_bounds__(256) accumulate_peers_u64(unsigned long long* __restrict__ dst, const PeerImages peers, size_t n2) {
+  // two tallies per thread and iteration: 16-byte loads over NVLink, one read-modify-write of the local image
+  ulonglong2* d2 = reinterpret_cast<ulonglong2*>(dst);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) {
+    ulonglong2 acc = d2[i];
+#pragma unroll 1
+    for (int k = 0; k < peers.n; k++) {
+      const ulonglong2 v = reinterpret_cast<const ulonglong2*>(peers.src[k])[i];
+      acc.x += v.x, acc.y += v.y;
+    }
+    d2[i] = acc;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -63,6 +85,7 @@ static void free_scene_allocs(mcgpu_device* d) {
   d->d_materials_dose = NULL, d->d_voxels_edep = NULL;
   d->d_stream_counter = NULL;
   if (d->h_stage) cudaFreeHost(d->h_stage);
+  mcgpu_dev_pipeline_end(d);
   d->d_volume = NULL, d->d_palette = NULL, d->d_mfp = NULL, d->d_woodcock = NULL, d->d_ray_xpab = NULL;
   d->d_ray_itl_itu = NULL, d->d_cmp_shells = NULL, d->d_spectrum = NULL, d->d_image = NULL, d->d_peer_stage = NULL, d->h_stage = NULL;
 }
@@ -175,6 +198,7 @@ extern "C" int mcgpu_dev_sync(struct mcgpu_device* d, float* kernel_ms, char* er
     unsigned long long flag = 0;
     CK(cudaMemcpy(&flag, d->d_stream_counter + 1, sizeof flag, cudaMemcpyDeviceToHost));
     if (flag) {
+      CK(cudaMemset(d->d_stream_counter + 1, 0, sizeof flag));
       snprintf(err, errlen, "device %d: wavefront transport kernel watchdog fired (code %llu)", d->ordinal, flag & 0xffffffffull);
       return -1;
     }
@@ -189,25 +213,265 @@ extern "C" int mcgpu_dev_fetch(struct mcgpu_device* d, uint64_t* host, char* err
   return 0;
 }
 
-extern "C" int mcgpu_dev_accumulate_peer(struct mcgpu_device* dst, struct mcgpu_device* src, char* err, size_t errlen) {
-  int can = 0;
-  CK(cudaSetDevice(dst->ordinal));
-  CK(cudaDeviceCanAccessPeer(&can, dst->ordinal, src->ordinal));
-  const size_t n = dst->image_words;
-  const unsigned long long* from = src->d_image;
-  if (can) {
-    cudaError_t e = cudaDeviceEnablePeerAccess(src->ordinal, 0);
-    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) can = 0;
-    cudaGetLastError();
+// ---- reducer -------------------------------------------------------------------------------------------------
+#include <dlfcn.h>
+#include <nccl.h>  // types and prototypes only: libnccl is opened at run time, the library has no link-time dependency on it
+
+struct NcclApi {
+  void* handle;
+  ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*);
+  ncclResult_t (*CommDestroy)(ncclComm_t);
+  ncclResult_t (*GroupStart)(void);
+  ncclResult_t (*GroupEnd)(void);
+  ncclResult_t (*Reduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t);
+  const char* (*GetErrorString)(ncclResult_t);
+};
+
+static const NcclApi* nccl_api(void) {
+  static NcclApi api;
+  static int state = 0;  // 0 untried, 1 loaded, -1 unavailable
+  if (state == 0) {
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (size_t i = 0; i < sizeof names / sizeof names[0] && !api.handle; i++) api.handle = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+    state = -1;
+    if (api.handle) {
+      api.CommInitAll = (decltype(api.CommInitAll))dlsym(api.handle, "ncclCommInitAll");
+      api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.handle, "ncclCommDestroy");
+      api.GroupStart = (decltype(api.GroupStart))dlsym(api.handle, "ncclGroupStart");
+      api.GroupEnd = (decltype(api.GroupEnd))dlsym(api.handle, "ncclGroupEnd");
+      api.Reduce = (decltype(api.Reduce))dlsym(api.handle, "ncclReduce");
+      api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.handle, "ncclGetErrorString");
+      if (api.CommInitAll && api.CommDestroy && api.GroupStart && api.GroupEnd && api.Reduce && api.GetErrorString) state = 1;
+    }
   }
-  if (!can) {  // no NVLink/P2P path: stage through a device-to-device copy
-    if (!dst->d_peer_stage) CK(cudaMalloc((void**)&dst->d_peer_stage, sizeof(unsigned long long) * n));
-    CK(cudaMemcpyPeerAsync(dst->d_peer_stage, dst->ordinal, src->d_image, src->ordinal, sizeof(unsigned long long) * n, dst->stream));
-    from = dst->d_peer_stage;
+  return state == 1 ? &api : NULL;
+}
+
+struct mcgpu_reducer {
+  int n;
+  int mode;  // 1 = ncclReduce, 2 = one-pass peer kernel, 3 = staged copies (no peer access)
+  struct mcgpu_device* dev[MCGPU_MAX_PEERS];
+  ncclComm_t comm[MCGPU_MAX_PEERS];
+  cudaEvent_t ready[MCGPU_MAX_PEERS];  // peer kernel: the source images are complete
+  cudaEvent_t t0, t1;
+};
+
+extern "C" void mcgpu_dev_reducer_free(struct mcgpu_reducer* r) {
+  if (!r) return;
+  const NcclApi* api = nccl_api();
+  for (int k = 0; k < r->n; k++) {
+    cudaSetDevice(r->dev[k]->ordinal);
+    if (r->mode == 1 && api && r->comm[k]) api->CommDestroy(r->comm[k]);
+    if (r->ready[k]) cudaEventDestroy(r->ready[k]);
   }
-  accumulate_u64<<<dst->sm_count * 4, 256, 0, dst->stream>>>(dst->d_image, from, n);
-  CK(cudaGetLastError());
-  CK(cudaStreamSynchronize(dst->stream));
+  if (r->n > 0) {
+    cudaSetDevice(r->dev[0]->ordinal);
+    if (r->t0) cudaEventDestroy(r->t0);
+    if (r->t1) cudaEventDestroy(r->t1);
+  }
+  free(r);
+}
+
+extern "C" const char* mcgpu_dev_reducer_kind(const struct mcgpu_reducer* r) {
+  return !r ? "none" : r->mode == 1 ? "ncclReduce" : r->mode == 2 ? "peer-kernel" : "staged-copy";
+}
+
+// Set up the reduction of the images of devs[0..n) onto devs[0].
+extern "C" struct mcgpu_reducer* mcgpu_dev_reducer_create(struct mcgpu_device** devs, int n, char* err, size_t errlen) {
+  if (n < 2 || n > MCGPU_MAX_PEERS) {
+    snprintf(err, errlen, "reducer: %d devices (2..%d supported)", n, MCGPU_MAX_PEERS);
+    return NULL;
+  }
+  mcgpu_reducer* r = (mcgpu_reducer*)calloc(1, sizeof *r);
+  if (!r) return NULL;
+  r->n = n;
+  for (int k = 0; k < n; k++) r->dev[k] = devs[k];
+  const char* want = getenv("MCGPU_REDUCE");  // "nccl" (default) | "peer"
+  const NcclApi* api = (want && !strcmp(want, "peer")) ? NULL : nccl_api();
+  if (api) {
+    int ids[MCGPU_MAX_PEERS];
+    for (int k = 0; k < n; k++) ids[k] = devs[k]->ordinal;
+    const ncclResult_t rc = api->CommInitAll(r->comm, n, ids);
+    if (rc == ncclSuccess)
+      r->mode = 1;
+    else if (want && !strcmp(want, "nccl")) {
+      snprintf(err, errlen, "reducer: ncclCommInitAll failed: %s", api->GetErrorString(rc));
+      free(r);
+      return NULL;
+    }
+  } else if (want && !strcmp(want, "nccl")) {
+    snprintf(err, errlen, "reducer: MCGPU_REDUCE=nccl but libnccl.so.2 cannot be loaded");
+    free(r);
+    return NULL;
+  }
+  if (r->mode == 0) {  // peer mappings for the one-pass kernel
+    r->mode = 2;
+    cudaSetDevice(devs[0]->ordinal);
+    for (int k = 1; k < n; k++) {
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, devs[0]->ordinal, devs[k]->ordinal);
+      if (can) {
+        const cudaError_t e = cudaDeviceEnablePeerAccess(devs[k]->ordinal, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) can = 0;
+        cudaGetLastError();
+      }
+      if (!can) r->mode = 3;
+    }
+  }
+  for (int k = 0; k < n; k++) {
+    cudaSetDevice(devs[k]->ordinal);
+    if (cudaEventCreateWithFlags(&r->ready[k], cudaEventDisableTiming) != cudaSuccess) {
+      snprintf(err, errlen, "reducer: cannot create events");
+      mcgpu_dev_reducer_free(r);
+      return NULL;
+    }
+  }
+  cudaSetDevice(devs[0]->ordinal);
+  if (cudaEventCreate(&r->t0) != cudaSuccess || cudaEventCreate(&r->t1) != cudaSuccess) {
+    snprintf(err, errlen, "reducer: cannot create events");
+    mcgpu_dev_reducer_free(r);
+    return NULL;
+  }
+  return r;
+}
+
+// Sum the images of all devices of the reducer onto the first one.  Enqueued behind whatever is in the devices' streams
+// (the transport kernels); returns after the sum is complete, *reduce_ms = device time of the reduction on device 0.
+extern "C" int mcgpu_dev_reduce(struct mcgpu_reducer* r, float* reduce_ms, char* err, size_t errlen) {
+  mcgpu_device* root = r->dev[0];
+  const size_t n = root->image_words;
+  for (int k = 1; k < r->n; k++)
+    if (r->dev[k]->image_words != n) {
+      snprintf(err, errlen, "reducer: device images differ in size");
+      return -1;
+    }
+  if (r->mode == 1) {
+    const NcclApi* api = nccl_api();
+    // the root's clock starts when ITS transport kernel is done; the collective itself waits for the slowest device
+    CK(cudaSetDevice(root->ordinal));
+    CK(cudaEventRecord(r->t0, root->stream));
+    ncclResult_t rc = api->GroupStart();
+    for (int k = 0; k < r->n && rc == ncclSuccess; k++)
+      rc = api->Reduce(r->dev[k]->d_image, r->dev[k]->d_image, n, ncclUint64, ncclSum, 0, r->comm[k], r->dev[k]->stream);
+    const ncclResult_t rc2 = api->GroupEnd();
+    if (rc != ncclSuccess || rc2 != ncclSuccess) {
+      snprintf(err, errlen, "reducer: ncclReduce failed: %s", api->GetErrorString(rc != ncclSuccess ? rc : rc2));
+      return -1;
+    }
+    CK(cudaSetDevice(root->ordinal));
+    CK(cudaEventRecord(r->t1, root->stream));
+    for (int k = 0; k < r->n; k++) {
+      CK(cudaSetDevice(r->dev[k]->ordinal));
+      CK(cudaStreamSynchronize(r->dev[k]->stream));
+    }
+  } else {
+    for (int k = 1; k < r->n; k++) {  // the root's stream waits until every peer image is complete
+      CK(cudaSetDevice(r->dev[k]->ordinal));
+      CK(cudaEventRecord(r->ready[k], r->dev[k]->stream));
+    }
+    CK(cudaSetDevice(root->ordinal));
+    for (int k = 1; k < r->n; k++) CK(cudaStreamWaitEvent(root->stream, r->ready[k], 0));
+    CK(cudaEventRecord(r->t0, root->stream));
+    if (r->mode == 2) {
+      PeerImages peers;
+      peers.n = r->n - 1;
+      for (int k = 1; k < r->n; k++) peers.src[k - 1] = r->dev[k]->d_image;
+      accumulate_peers_u64<<<root->sm_count * 8, 256, 0, root->stream>>>(root->d_image, peers, n / 2);  // image_words = 4*Npix: even
+      CK(cudaGetLastError());
+    } else {  // no peer access: stage each image through a device-to-device copy
+      if (!root->d_peer_stage) CK(cudaMalloc((void**)&root->d_peer_stage, sizeof(unsigned long long) * n));
+      for (int k = 1; k < r->n; k++) {
+        PeerImages peers;
+        peers.n = 1, peers.src[0] = root->d_peer_stage;
+        CK(cudaMemcpyPeerAsync(root->d_peer_stage, root->ordinal, r->dev[k]->d_image, r->dev[k]->ordinal, sizeof(unsigned long long) * n, root->stream));
+        accumulate_peers_u64<<<root->sm_count * 8, 256, 0, root->stream>>>(root->d_image, peers, n / 2);
+        CK(cudaGetLastError());
+      }
+    }
+    CK(cudaEventRecord(r->t1, root->stream));
+    CK(cudaStreamSynchronize(root->stream));
+  }
+  if (reduce_ms) {
+    CK(cudaSetDevice(root->ordinal));
+    CK(cudaEventSynchronize(r->t1));
+    CK(cudaEventElapsedTime(reduce_ms, r->t0, r->t1));
+  }
+  return 0;
+}
+
+
+// ---- pipelined scan ------------------------------------------------------------------------------------------
+// The reference's loop serialises kernel, device->host copy and report (H:861-1040).  Here a device owns two images and
+// two pinned host buffers: while projection p is transported into one image, the other one (projection p-1) travels to
+// the host on a second stream and is formatted by the host thread (api.c: scan_thread), so the GPU never waits.
+extern "C" void mcgpu_dev_pipeline_end(struct mcgpu_device* d) {
+  if (!d || !d->pipeline_on) return;
+  cudaSetDevice(d->ordinal);
+  cudaStreamSynchronize(d->stream);
+  if (d->copy_stream) cudaStreamSynchronize(d->copy_stream), cudaStreamDestroy(d->copy_stream);
+  cudaFree(d->d_image_alt);
+  for (int k = 0; k < 2; k++) {
+    if (d->h_pinned[k]) cudaFreeHost(d->h_pinned[k]);
+    if (d->p_ev0[k]) cudaEventDestroy(d->p_ev0[k]);
+    if (d->p_ev1[k]) cudaEventDestroy(d->p_ev1[k]);
+    if (d->p_copied[k]) cudaEventDestroy(d->p_copied[k]);
+    d->h_pinned[k] = NULL, d->p_ev0[k] = NULL, d->p_ev1[k] = NULL, d->p_copied[k] = NULL;
+  }
+  if (d->h_flag) cudaFreeHost(d->h_flag);
+  d->h_flag = NULL, d->d_image_alt = NULL, d->copy_stream = NULL, d->pipeline_on = 0;
+}
+
+extern "C" int mcgpu_dev_pipeline_begin(struct mcgpu_device* d, char* err, size_t errlen) {
+  CK(cudaSetDevice(d->ordinal));
+  if (d->pipeline_on) return 0;
+  if (!d->d_image) {
+    snprintf(err, errlen, "device %d: nothing uploaded", d->ordinal);
+    return -1;
+  }
+  d->pipeline_on = 1;
+  const size_t bytes = sizeof(unsigned long long) * d->image_words;
+  CK(cudaMalloc((void**)&d->d_image_alt, bytes));
+  CK(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
+  CK(cudaHostAlloc((void**)&d->h_flag, 2 * sizeof(unsigned long long), cudaHostAllocDefault));
+  for (int k = 0; k < 2; k++) {
+    CK(cudaHostAlloc((void**)&d->h_pinned[k], bytes, cudaHostAllocDefault));
+    CK(cudaEventCreate(&d->p_ev0[k]));
+    CK(cudaEventCreate(&d->p_ev1[k]));
+    CK(cudaEventCreateWithFlags(&d->p_copied[k], cudaEventDisableTiming));
+    CK(cudaEventRecord(d->p_copied[k], d->copy_stream));  // "nothing pending" for the first use of the slot
+  }
+  return 0;
+}
+
+extern "C" int mcgpu_dev_pipeline_launch(struct mcgpu_device* d, const mcgpu_view* view, const mcgpu_launch* l, char* err, size_t errlen) {
+  const int slot = l->image_slot & 1;
+  CK(cudaSetDevice(d->ordinal));
+  if (!d->pipeline_on) {
+    snprintf(err, errlen, "device %d: pipeline not started", d->ordinal);
+    return -1;
+  }
+  CK(cudaStreamWaitEvent(d->stream, d->p_copied[slot], 0));  // the slot's previous image has left the device
+  CK(cudaEventRecord(d->p_ev0[slot], d->stream));
+  if (mcgpu_dev_launch(d, view, l, err, errlen) != 0) return -1;
+  // mcgpu_dev_launch bracketed the kernel with ev0/ev1 on d->stream; per-slot events keep the time of THIS projection
+  CK(cudaEventRecord(d->p_ev1[slot], d->stream));
+  CK(cudaStreamWaitEvent(d->copy_stream, d->p_ev1[slot], 0));
+  CK(cudaMemcpyAsync(d->h_pinned[slot], slot ? d->d_image_alt : d->d_image, sizeof(unsigned long long) * d->image_words, cudaMemcpyDeviceToHost, d->copy_stream));
+  CK(cudaMemcpyAsync(d->h_flag, d->d_stream_counter + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, d->copy_stream));
+  CK(cudaEventRecord(d->p_copied[slot], d->copy_stream));
+  return 0;
+}
+
+extern "C" int mcgpu_dev_pipeline_wait(struct mcgpu_device* d, int slot, float* kernel_ms, uint64_t** host, char* err, size_t errlen) {
+  slot &= 1;
+  CK(cudaSetDevice(d->ordinal));
+  CK(cudaEventSynchronize(d->p_copied[slot]));
+  if (kernel_ms) CK(cudaEventElapsedTime(kernel_ms, d->p_ev0[slot], d->p_ev1[slot]));
+  if (d->h_flag && d->h_flag[0]) {
+    snprintf(err, errlen, "device %d: wavefront transport kernel watchdog fired (code %d)", d->ordinal, d->h_flag[0]);
+    return -1;
+  }
+  if (host) *host = d->h_pinned[slot];
   return 0;
 }
 

@@ -51,6 +51,14 @@ struct mcgpu_device {
   int wf_block;                          // wavefront kernel: threads per CTA (512: two CTAs per SM, 1024: one)
   int fast_math;                         // 0 = bit-exact arithmetic (default), 1 = the reference's shipped -use_fast_math flags
   uint64_t* h_stage;
+  // pipelined scan (mcgpu_dev_pipeline_*): a second image and a copy stream, so that the device->host copy of one
+  // projection overlaps the transport of the next; slot 0 is d_image
+  unsigned long long* d_image_alt;
+  uint64_t* h_pinned[2];
+  cudaStream_t copy_stream;
+  cudaEvent_t p_ev0[2], p_ev1[2], p_copied[2];
+  int* h_flag;  // pinned copy of the kernel error flag
+  int pipeline_on;
   void* post_ws;                         // workspace of the post-processing kernels (postprocess.cu)
   size_t post_ws_bytes;
   int timed;

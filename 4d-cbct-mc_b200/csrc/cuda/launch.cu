@@ -29,6 +29,7 @@ struct LaunchArgs {
   const mcgpu_launch* l;
   long long n_streams;
   int g1, g2;
+  SceneDev scene;  // the device's scene with the image pointer of the launch's slot
 };
 
 // The product kernel: persistent grid, one or two CTAs per SM, shared memory split between the Compton scratch and the photon pool.
@@ -62,9 +63,9 @@ int launch_wavefront(const LaunchArgs& a, char* err, size_t errlen) {
   long long pgrid = (long long)d->sm_count * (per_sm > 0 ? per_sm : 1);
   const long long useful = (a.n_streams + pool - 1) / pool;
   if (pgrid > useful) pgrid = useful;
-  CK(cudaMemsetAsync(d->d_stream_counter, 0, 2 * sizeof(unsigned long long), d->stream));
+  CK(cudaMemsetAsync(d->d_stream_counter, 0, sizeof(unsigned long long), d->stream));  // [1], the error flag, is sticky until read
   transport_wavefront<BITS, DOSE, ROT><<<(unsigned)pgrid, wblock, wsmem, d->stream>>>(
-      d->scene, *a.view, a.l->stream_begin, a.l->stream_end, a.l->histories_per_thread, a.l->seed_input, a.g1, a.g2, d->d_stream_counter, d->w_threshold, pool, pal, rows,
+      a.scene, *a.view, a.l->stream_begin, a.l->stream_end, a.l->histories_per_thread, a.l->seed_input, a.g1, a.g2, d->d_stream_counter, d->w_threshold, pool, pal, rows,
       reinterpret_cast<int*>(d->d_stream_counter + 1));
   return 0;
 }
@@ -82,7 +83,7 @@ int launch_regroup(const LaunchArgs& a, size_t smem, char* err, size_t errlen) {
   const long long grid = (a.n_streams + block - 1) / block;
   if (pgrid > grid) pgrid = grid;
   CK(cudaMemsetAsync(d->d_stream_counter, 0, sizeof(unsigned long long), d->stream));
-  transport_regroup<BITS, DOSE, ROT><<<(unsigned)pgrid, block, smem, d->stream>>>(d->scene, *a.view, a.l->stream_begin, a.l->stream_end, a.l->histories_per_thread,
+  transport_regroup<BITS, DOSE, ROT><<<(unsigned)pgrid, block, smem, d->stream>>>(a.scene, *a.view, a.l->stream_begin, a.l->stream_end, a.l->histories_per_thread,
                                                                                    a.l->seed_input, a.g1, a.g2, d->d_stream_counter, d->w_threshold);
   return 0;
 }
@@ -110,7 +111,7 @@ int launch_bits(const LaunchArgs& a, char* err, size_t errlen) {
   const int block = 128;
   const long long grid = (a.n_streams + block - 1) / block;
   CK(cudaFuncSetAttribute(transport_streams<BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  transport_streams<BITS><<<(unsigned)grid, block, smem, d->stream>>>(d->scene, *a.view, a.l->stream_begin, a.l->stream_end, a.l->histories_per_thread, a.l->seed_input, a.g1,
+  transport_streams<BITS><<<(unsigned)grid, block, smem, d->stream>>>(a.scene, *a.view, a.l->stream_begin, a.l->stream_end, a.l->histories_per_thread, a.l->seed_input, a.g1,
                                                                       a.g2);
   return 0;
 #else
@@ -126,9 +127,16 @@ extern "C" int MCGPU_LAUNCH_NAME(struct mcgpu_device* d, const mcgpu_view* view,
     snprintf(err, errlen, "device %d: nothing uploaded", d->ordinal);
     return -1;
   }
-  if (l->zero_image) CK(cudaMemsetAsync(d->d_image, 0, sizeof(unsigned long long) * d->image_words, d->stream));
+  unsigned long long* image = l->image_slot ? d->d_image_alt : d->d_image;
+  if (!image) {
+    snprintf(err, errlen, "device %d: image slot %d is not allocated", d->ordinal, l->image_slot);
+    return -1;
+  }
+  if (l->zero_image) CK(cudaMemsetAsync(image, 0, sizeof(unsigned long long) * d->image_words, d->stream));
   LaunchArgs a;
   a.d = d, a.view = view, a.l = l;
+  a.scene = d->scene;
+  a.scene.image = image;
   a.n_streams = l->stream_end - l->stream_begin;
   CK(cudaEventRecord(d->ev0, d->stream));
   if (a.n_streams > 0) {

@@ -48,6 +48,7 @@ mcgpu_ctx* mcgpu_create(const int* device_ids, int n_devices) {
 void mcgpu_destroy(mcgpu_ctx* ctx) {
   int i;
   if (!ctx) return;
+  mcgpu_dev_reducer_free(ctx->reducer);
   for (i = 0; i < ctx->num_devices; i++) mcgpu_dev_close(ctx->dev[i]);
   free(ctx->dev);
   free(ctx->views);
@@ -173,6 +174,7 @@ static int launch_on(mcgpu_ctx* ctx, int d, int p, long long b, long long e, int
   l.stream_begin = b;
   l.stream_end = e;
   l.zero_image = 1;
+  l.image_slot = 0;
   return mcgpu_dev_launch(ctx->dev[d], &ctx->views[p], &l, ctx->err, sizeof ctx->err) == 0 ? MCGPU_OK : MCGPU_E_CUDA;
 }
 
@@ -212,15 +214,35 @@ int mcgpu_run_projection(mcgpu_ctx* ctx, int p, uint64_t* image_host) {
     if (ms > ms_max) ms_max = ms;
   }
   ctx->last_kernel_ms = ms_max;
-  /* integer tallies: summing the partial images in any order is bit-identical to one device */
-  for (d = 1; d < n; d++)
-    if (mcgpu_dev_accumulate_peer(ctx->dev[0], ctx->dev[d], ctx->err, sizeof ctx->err) != 0) return MCGPU_E_CUDA;
+  ctx->last_reduce_ms = 0.0;
+  if (n > 1) { /* integer tallies: summing the partial images in any order is bit-identical to one device (the reference: MPI_Reduce, H:1019) */
+    float rms = 0.f;
+    if (ctx->reducer && ctx->reducer_devices != n) {
+      mcgpu_dev_reducer_free(ctx->reducer);
+      ctx->reducer = NULL;
+    }
+    if (!ctx->reducer) {
+      ctx->reducer = mcgpu_dev_reducer_create(ctx->dev, n, ctx->err, sizeof ctx->err);
+      ctx->reducer_devices = n;
+      if (!ctx->reducer) return MCGPU_E_CUDA;
+    }
+    if (mcgpu_dev_reduce(ctx->reducer, &rms, ctx->err, sizeof ctx->err) != 0) return MCGPU_E_CUDA;
+    ctx->last_reduce_ms = rms;
+  }
   if (image_host && mcgpu_dev_fetch(ctx->dev[0], image_host, ctx->err, sizeof ctx->err) != 0) return MCGPU_E_CUDA;
   return MCGPU_OK;
 }
 
 void* mcgpu_device_image(mcgpu_ctx* ctx) { return (ctx && ctx->num_devices > 0) ? mcgpu_dev_image_ptr(ctx->dev[0]) : NULL; }
 double mcgpu_last_kernel_ms(const mcgpu_ctx* ctx) { return ctx ? ctx->last_kernel_ms : 0.0; }
+double mcgpu_last_reduce_ms(const mcgpu_ctx* ctx) { return ctx ? ctx->last_reduce_ms : 0.0; }
+const char* mcgpu_reduce_kind(const mcgpu_ctx* ctx) { return ctx ? mcgpu_dev_reducer_kind(ctx->reducer) : "none"; }
+int mcgpu_get_scan_stats(const mcgpu_ctx* ctx, double* out, int n) {
+  int k;
+  if (!ctx || !out) return MCGPU_E_ARG;
+  for (k = 0; k < n && k < MCGPU_SCAN_STATS; k++) out[k] = ctx->scan_stats[k];
+  return k;
+}
 
 /* ---- whole scan: projections dealt round-robin to the devices, one host thread per device ---- */
 
@@ -237,6 +259,9 @@ typedef struct scan_shared {
 typedef struct scan_worker {
   scan_shared* sh;
   int device, started;
+  /* where this device's host thread spent the scan (mcgpu_get_scan_stats) */
+  double kernel_ms, t_wait, t_report;
+  int projections;
   char err[512];
 } scan_worker;
 
@@ -248,29 +273,37 @@ static void scan_publish(scan_shared* sh, int p, int status, double dt) {
   pthread_mutex_unlock(&sh->mu);
 }
 
-/* One host thread per device.  The projection loop is software-pipelined: while the GPU transports
- * projection p the thread formats and writes the ASCII file of its previous projection (64 MB of
- * text, ~0.1 s), so reporting costs no GPU time (the reference serialises kernel and fprintf, H:861-1040). */
+/* One host thread per device.  The projection loop is software-pipelined three deep: while the GPU transports
+ * projection p into one of its two images, the other image (projection p-1) is copied to a pinned host buffer on a second
+ * stream and this thread formats and writes its ASCII file (63 MB of text, ~0.1 s), so neither the copy nor the report
+ * costs GPU time (the reference serialises kernel, copy and fprintf, H:861-1040). */
+static int scan_report(scan_worker* w, int p, const uint64_t* image, double dt) {
+  scan_shared* sh = w->sh;
+  mcgpu_ctx* ctx = sh->ctx;
+  const double t0 = now_s();
+  int rc = mcgpu_write_projection_ascii(ctx, p, image, dt);
+  if (rc == MCGPU_OK && sh->write_raw) rc = mcgpu_write_projection_raw(ctx, p, image);
+  w->t_report += now_s() - t0;
+  if (rc != MCGPU_OK) snprintf(w->err, sizeof w->err, "%s", ctx->err);
+  scan_publish(sh, p, rc == MCGPU_OK ? 1 : rc, dt);
+  return rc;
+}
+
 static void* scan_thread(void* arg) {
   scan_worker* w = (scan_worker*)arg;
   scan_shared* sh = w->sh;
   mcgpu_ctx* ctx = sh->ctx;
+  struct mcgpu_device* dev = ctx->dev[w->device];
   const int P = ctx->in.num_projections, n = ctx->num_devices;
-  const size_t words = (size_t)4 * ctx->views[0].total_num_pixels;
-  uint64_t* image[2];
-  int p, cur = 0, prev = -1, failed = 0;
-  double prev_dt = 0.0;
-  image[0] = (uint64_t*)malloc(words * sizeof(uint64_t));
-  image[1] = (uint64_t*)malloc(words * sizeof(uint64_t));
+  int p, slot = 0, prev = -1, prev_slot = 0, failed = 0;
+  double prev_t0 = 0.0;
+  if (mcgpu_dev_pipeline_begin(dev, w->err, sizeof w->err) != 0) {
+    for (p = w->device; p < P; p += n) scan_publish(sh, p, MCGPU_E_CUDA, 0.0);
+    return NULL;
+  }
   for (p = w->device; p < P && !failed; p += n) {
-    double t0 = now_s();
-    float ms;
+    const double t0 = now_s();
     int launched = 0;
-    if (!image[0] || !image[1]) {
-      snprintf(w->err, sizeof w->err, "out of memory for the host image");
-      scan_publish(sh, p, MCGPU_E_NOMEM, 0.0);
-      break;
-    }
     if (projection_skipped(ctx, p)) {
       scan_publish(sh, p, 2, 0.0);
     } else {
@@ -281,39 +314,47 @@ static void* scan_thread(void* arg) {
       l.stream_begin = 0;
       l.stream_end = (long long)sh->blocks * ctx->in.threads_per_block;
       l.zero_image = 1;
-      if (mcgpu_dev_launch(ctx->dev[w->device], &ctx->views[p], &l, w->err, sizeof w->err) != 0) {
+      l.image_slot = slot;
+      if (mcgpu_dev_pipeline_launch(dev, &ctx->views[p], &l, w->err, sizeof w->err) != 0) {
         scan_publish(sh, p, MCGPU_E_CUDA, 0.0);
         failed = 1;
       } else
         launched = 1;
     }
-    if (prev >= 0) { /* overlapped with the kernel just launched */
-      int rc = mcgpu_write_projection_ascii(ctx, prev, image[cur ^ 1], prev_dt);
-      if (rc == MCGPU_OK && sh->write_raw) rc = mcgpu_write_projection_raw(ctx, prev, image[cur ^ 1]);
-      if (rc != MCGPU_OK) snprintf(w->err, sizeof w->err, "%s", ctx->err);
-      scan_publish(sh, prev, rc == MCGPU_OK ? 1 : rc, prev_dt);
-      if (rc != MCGPU_OK) failed = 1;
+    if (prev >= 0) { /* the previous projection: wait for its copy, report it while the kernel just launched runs */
+      uint64_t* host = NULL;
+      float ms = 0.f;
+      const double tw = now_s();
+      if (mcgpu_dev_pipeline_wait(dev, prev_slot, &ms, &host, w->err, sizeof w->err) != 0) {
+        scan_publish(sh, prev, MCGPU_E_CUDA, 0.0);
+        failed = 1;
+      } else {
+        w->t_wait += now_s() - tw;
+        w->kernel_ms += ms;
+        w->projections++;
+        if (scan_report(w, prev, host, now_s() - prev_t0) != MCGPU_OK) failed = 1;
+      }
       prev = -1;
     }
     if (launched) {
-      if (mcgpu_dev_sync(ctx->dev[w->device], &ms, w->err, sizeof w->err) != 0 || mcgpu_dev_fetch(ctx->dev[w->device], image[cur], w->err, sizeof w->err) != 0) {
-        scan_publish(sh, p, MCGPU_E_CUDA, 0.0);
-        failed = 1;
-      } else {
-        prev = p;
-        prev_dt = now_s() - t0;
-        cur ^= 1;
-      }
+      prev = p, prev_slot = slot, prev_t0 = t0;
+      slot ^= 1;
     }
   }
   if (prev >= 0) {
-    int rc = mcgpu_write_projection_ascii(ctx, prev, image[cur ^ 1], prev_dt);
-    if (rc == MCGPU_OK && sh->write_raw) rc = mcgpu_write_projection_raw(ctx, prev, image[cur ^ 1]);
-    if (rc != MCGPU_OK) snprintf(w->err, sizeof w->err, "%s", ctx->err);
-    scan_publish(sh, prev, rc == MCGPU_OK ? 1 : rc, prev_dt);
+    uint64_t* host = NULL;
+    float ms = 0.f;
+    const double tw = now_s();
+    if (mcgpu_dev_pipeline_wait(dev, prev_slot, &ms, &host, w->err, sizeof w->err) != 0)
+      scan_publish(sh, prev, MCGPU_E_CUDA, 0.0);
+    else {
+      w->t_wait += now_s() - tw;
+      w->kernel_ms += ms;
+      w->projections++;
+      scan_report(w, prev, host, now_s() - prev_t0);
+    }
   }
-  free(image[0]);
-  free(image[1]);
+  mcgpu_dev_pipeline_end(dev);
   return NULL;
 }
 
@@ -349,6 +390,7 @@ int mcgpu_run_all(mcgpu_ctx* ctx, mcgpu_progress_cb cb, void* user) {
     pthread_t* threads = (pthread_t*)calloc((size_t)n, sizeof *threads);
     int d, seed, hpt, blocks, verbose = ctx->verbose;
     unsigned long long launched;
+    const double t_scan0 = now_s();
     memset(&sh, 0, sizeof sh);
     sh.ctx = ctx;
     sh.write_raw = getenv("MCGPU_WRITE_RAW") && atoi(getenv("MCGPU_WRITE_RAW")) != 0;
@@ -412,6 +454,15 @@ int mcgpu_run_all(mcgpu_ctx* ctx, mcgpu_progress_cb cb, void* user) {
     for (d = 0; d < n; d++)
       if (workers[d].started) pthread_join(threads[d], NULL);
     ctx->verbose = verbose;
+    memset(ctx->scan_stats, 0, sizeof ctx->scan_stats);
+    ctx->scan_stats[0] = now_s() - t_scan0;
+    for (d = 0; d < n; d++) {
+      ctx->scan_stats[1] += 1e-3 * workers[d].kernel_ms;
+      ctx->scan_stats[2] += workers[d].t_wait;
+      ctx->scan_stats[3] += workers[d].t_report;
+      ctx->scan_stats[4] += workers[d].projections;
+    }
+    ctx->scan_stats[5] = n;
     if (rc != MCGPU_OK)
       for (d = 0; d < n; d++)
         if (workers[d].err[0]) snprintf(ctx->err, sizeof ctx->err, "%s", workers[d].err);

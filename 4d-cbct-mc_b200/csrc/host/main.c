@@ -92,6 +92,13 @@ static int simulate_one(mcgpu_ctx* ctx, const struct timespec* t0) {
   printf("          >>> Execution time including initialization, transport and report: %.3f s.\n", t_total);
   printf("          >>> Time spent in the Monte Carlo transport and reporting: %.3f s.\n", t_total - t_init);
   printf("          >>> Total number of simulated x rays:  %llu\n", info.launched_histories * (unsigned long long)info.num_projections);
+  {
+    double st[6] = {0, 0, 0, 0, 0, 0};
+    if (mcgpu_get_scan_stats(ctx, st, 6) == 6 && st[4] > 0.0) /* projection-parallel scans only */
+      printf("          >>> Projection loop: %.3f s wall for %.0f projections on %.0f device(s) = %.4f s per projection; per device thread: "
+             "%.3f s in transport kernels, %.3f s waiting for kernel + device->host copy, %.3f s formatting and writing reports\n",
+             st[0], st[4], st[5], st[0] / st[4], st[1] / st[5], st[2] / st[5], st[3] / st[5]);
+  }
   if (t_total > 0.000001)
     printf("          >>> Total speed (including initialization time) [x-rays/s]:  %.2f\n\n", (double)(info.launched_histories * (unsigned long long)info.num_projections) / t_total);
   fflush(stdout);

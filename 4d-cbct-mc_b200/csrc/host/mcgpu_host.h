@@ -21,6 +21,7 @@ extern "C" {
 #define MCGPU_MAX_ENERGYBINS_RAYLEIGH 25005
 #define MCGPU_MAX_ENERGY_BINS 256
 #define MCGPU_LINE 250
+#define MCGPU_SCAN_STATS 8
 
 typedef struct { float x, y; } mcgpu_f2;
 typedef struct { float x, y, z; } mcgpu_f3;
@@ -144,7 +145,11 @@ struct mcgpu_ctx {
   int num_devices;
   struct mcgpu_device** dev;
   double last_kernel_ms;
+  double last_reduce_ms;            /* history-split runs: device time of the reduction of the partial images */
+  struct mcgpu_reducer* reducer;    /* created on the first multi-device projection, for reducer_devices devices */
+  int reducer_devices;
   int fast_math;
+  double scan_stats[MCGPU_SCAN_STATS]; /* mcgpu_run_all: summed over the devices' host threads, see mcgpu_get_scan_stats */
 };
 
 /* ---- host stages (each returns MCGPU_OK or an error code, message in ctx->err) ---------- */
@@ -169,6 +174,7 @@ typedef struct mcgpu_launch {
   int threads_per_block;
   long long stream_begin, stream_end; /* reference global thread ids */
   int zero_image;
+  int image_slot; /* 0 = the device's image, 1 = the second image of the pipelined scan */
 } mcgpu_launch;
 
 int mcgpu_dev_count(void);
@@ -180,9 +186,19 @@ int mcgpu_dev_upload(struct mcgpu_device* d, const mcgpu_scene* s, const mcgpu_v
 int mcgpu_dev_launch(struct mcgpu_device* d, const mcgpu_view* view, const mcgpu_launch* l, char* err, size_t errlen);
 int mcgpu_dev_sync(struct mcgpu_device* d, float* kernel_ms, char* err, size_t errlen);
 int mcgpu_dev_fetch(struct mcgpu_device* d, uint64_t* host, char* err, size_t errlen);
-/* dst += src over NVLink peer access (or staged copy when peer access is unavailable) */
-int mcgpu_dev_accumulate_peer(struct mcgpu_device* dst, struct mcgpu_device* src, char* err, size_t errlen);
+/* history-split reduction: sum of the devices' images on the first one -- ncclReduce over NVLink, or one kernel reading all peers */
+struct mcgpu_reducer;
+struct mcgpu_reducer* mcgpu_dev_reducer_create(struct mcgpu_device** devs, int n, char* err, size_t errlen);
+void mcgpu_dev_reducer_free(struct mcgpu_reducer* r);
+const char* mcgpu_dev_reducer_kind(const struct mcgpu_reducer* r);
+int mcgpu_dev_reduce(struct mcgpu_reducer* r, float* reduce_ms, char* err, size_t errlen);
 void* mcgpu_dev_image_ptr(struct mcgpu_device* d);
+/* pipelined scan: launch projection work into image slot 0/1 (asynchronous; the copy to a pinned host buffer is queued behind
+ * it on a second stream), wait for a slot's copy (kernel_ms = device time of its kernel, *host = the pinned buffer) */
+int mcgpu_dev_pipeline_begin(struct mcgpu_device* d, char* err, size_t errlen);
+int mcgpu_dev_pipeline_launch(struct mcgpu_device* d, const mcgpu_view* view, const mcgpu_launch* l, char* err, size_t errlen);
+int mcgpu_dev_pipeline_wait(struct mcgpu_device* d, int slot, float* kernel_ms, uint64_t** host, char* err, size_t errlen);
+void mcgpu_dev_pipeline_end(struct mcgpu_device* d);
 void mcgpu_dev_set_fast_math(struct mcgpu_device* d, int on);
 /* dose tallies accumulate over launches until reset; fetch ADDS the device's counters to the host arrays */
 int mcgpu_dev_reset_dose(struct mcgpu_device* d, char* err, size_t errlen);

@@ -51,6 +51,9 @@ _SIGS = {
     "mcgpu_run_streams": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.c_longlong, C.c_void_p]),
     "mcgpu_device_image": (C.c_void_p, [C.c_void_p]),
     "mcgpu_last_kernel_ms": (C.c_double, [C.c_void_p]),
+    "mcgpu_last_reduce_ms": (C.c_double, [C.c_void_p]),
+    "mcgpu_reduce_kind": (C.c_char_p, [C.c_void_p]),
+    "mcgpu_get_scan_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_int]),
     "mcgpu_run_all": (C.c_int, [C.c_void_p, PROGRESS_CB, C.c_void_p]),
     "mcgpu_write_projection_ascii": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_double]),
     "mcgpu_write_projection_raw": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
@@ -210,6 +213,20 @@ class Engine:
     @property
     def last_kernel_ms(self) -> float:
         return float(_lib.mcgpu_last_kernel_ms(self._h))
+
+    @property
+    def last_reduce_ms(self) -> float:
+        """History-split runs: device time of the reduction of the partial images (ncclReduce / peer kernel)."""
+        return float(_lib.mcgpu_last_reduce_ms(self._h))
+
+    @property
+    def reduce_kind(self) -> str:
+        return (_lib.mcgpu_reduce_kind(self._h) or b"none").decode()
+
+    def scan_stats(self) -> dict:
+        out = (C.c_double * 6)()
+        _lib.mcgpu_get_scan_stats(self._h, out, 6)
+        return dict(zip(("wall_s", "kernel_s", "wait_s", "report_s", "projections", "devices"), [float(v) for v in out]))
 
     @property
     def device_image_ptr(self) -> int:

@@ -119,6 +119,18 @@ void* mcgpu_device_image(mcgpu_ctx* ctx);
 /* Device time of the transport kernel(s) of the last run call, in ms (CUDA events on the launch stream). */
 double mcgpu_last_kernel_ms(const mcgpu_ctx* ctx);
 
+/* History-split runs (several devices, one projection): device time of the reduction of the partial images in the last
+ * mcgpu_run_projection, and how it was done: "ncclReduce" (libnccl over NVLink/NVSwitch; the reference: MPI_Reduce, H:1019),
+ * "peer-kernel" (one kernel reading every peer's image through NVLink peer mappings; when libnccl cannot be loaded or the
+ * environment has MCGPU_REDUCE=peer), "staged-copy" (no peer access) or "none". */
+double mcgpu_last_reduce_ms(const mcgpu_ctx* ctx);
+const char* mcgpu_reduce_kind(const mcgpu_ctx* ctx);
+
+/* Where the last mcgpu_run_all spent its time, summed over the devices' host threads: out[0] wall seconds of the loop,
+ * [1] device seconds in transport kernels, [2] host seconds waiting for kernel + device->host copy, [3] host seconds
+ * formatting and writing the reports, [4] projections simulated, [5] devices.  Returns the number of values written. */
+int mcgpu_get_scan_stats(const mcgpu_ctx* ctx, double* out, int n);
+
 /* The whole projection loop: projections are dealt round-robin to the devices (p -> p mod n),
  * each projection written with mcgpu_write_projection_ascii as soon as it is done, the
  * callback invoked in projection order.  With fewer projections than devices the
