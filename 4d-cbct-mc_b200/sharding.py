@@ -48,3 +48,23 @@ def as_int64_tensor(image_u64: np.ndarray, device=None):
 
     t = torch.from_numpy(image_u64.view(np.int64))
     return t.to(device) if device is not None else t
+
+
+class _DeviceImage:
+    """The engine's device tally (uint64[4*Npix], cudaMalloc'ed by libmcgpu_b200) exposed through
+    __cuda_array_interface__ as int64 (NCCL sums two's-complement words; same bits as the u64 sum)."""
+
+    def __init__(self, ptr: int, words: int):
+        self.__cuda_array_interface__ = {"shape": (words,), "typestr": "<i8", "data": (ptr, False), "version": 3, "strides": None}
+
+
+def device_tally_tensor(engine):
+    """Zero-copy torch view (int64, on the engine's GPU) of the tally the last run call left on the device --
+    what the one-process-per-GPU driver hands to torch.distributed.reduce (ncclReduce over NVLink)."""
+    import torch
+
+    info = engine.info
+    ptr = engine.device_image_ptr
+    if not ptr:
+        raise RuntimeError("the engine has no device image (no usable GPU)")
+    return torch.as_tensor(_DeviceImage(ptr, 4 * info.num_pixels_x * info.num_pixels_z), device="cuda")

@@ -25,7 +25,7 @@ ifeq ($(AB),1)
 NVFLAGS += -DMCGPU_AB_KERNELS
 endif
 
-all: lib exe oracle
+all: lib exe oracle ubench
 
 lib: $(LIBDIR)/libmcgpu_b200.so
 exe: $(BINDIR)/MC-GPU_v1.3.x $(BINDIR)/MC-GPU_v1.3_batch.x
@@ -68,8 +68,14 @@ $(BINDIR)/MC-GPU_v1.3_batch.x: $(HOSTDIR)/main.c $(LIBDIR)/libmcgpu_b200.so
 	@mkdir -p $(BINDIR)
 	$(CC) $(CFLAGS) -DMCGPU_BATCH_MAIN -fPIE $< -o $@ -L$(LIBDIR) -lmcgpu_b200 -lpthread -Wl,-rpath,'$$ORIGIN/../lib'
 
+# microbenchmarks that pin the hardware denominators of the rooflines (instruction cache, u64 atomics, L2 random gather)
+ubench: tools/ubench/bin/icache tools/ubench/bin/atomics tools/ubench/bin/l2gather
+tools/ubench/bin/%: tools/ubench/%.cu
+	@mkdir -p tools/ubench/bin
+	$(NVCC) -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -o $@ $<
+
 clean:
-	rm -rf $(BUILD) $(LIBDIR) $(BINDIR)
+	rm -rf $(BUILD) $(LIBDIR) $(BINDIR) tools/ubench/bin
 	$(MAKE) -C oracle clean
 
-.PHONY: all lib exe oracle clean
+.PHONY: all lib exe oracle ubench clean
