@@ -163,6 +163,12 @@ extern "C" int mcgpu_dev_upload(struct mcgpu_device* d, const mcgpu_scene* s, co
   for (int k = 0; k < 3; k++) {
     sc.inv_voxel[k] = v->inv_voxel_size[k];
     sc.bbox[k] = v->size_bbox[k];
+    {  // transport.cuh: locate_voxel_fast.  A box thinner than 2 EPS (0.3 um) contains nothing.
+      const float eps = 0.000015f, top = v->size_bbox[k] - eps;
+      unsigned be, bt;
+      memcpy(&be, &eps, 4), memcpy(&bt, &top, 4);
+      sc.box_hi[k] = ((bt > be && bt < 0x7f800000u) ? bt : be) - be;
+    }
   }
   sc.e0 = s->e0;
   sc.ide = s->ide;

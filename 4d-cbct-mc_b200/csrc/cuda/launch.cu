@@ -156,3 +156,69 @@ extern "C" int MCGPU_LAUNCH_NAME(struct mcgpu_device* d, const mcgpu_view* view,
   d->timed = 1;
   return 0;
 }
+
+#ifndef MCGPU_FAST_MATH
+// ---- device self tests of the arithmetic shortcuts of transport.cuh (exhaustive over their whole domain) ------------------
+namespace {
+__global__ void selftest_log_uniform(unsigned long long* mismatches) {  // every value RANECU can return: i2 in [1, 2147483562]
+  unsigned long long bad = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x + 1; i <= 2147483562ll; i += (long long)gridDim.x * blockDim.x) {
+    const float a = __int2float_rn((int)i) * 4.65661305739e-10f;
+    bad += __float_as_uint(log_uniform(a)) != __float_as_uint(logf(a));
+  }
+  if (bad) atomicAdd(mismatches, bad);
+}
+__global__ void selftest_rsqrt_normal(unsigned long long* mismatches) {  // every positive normal float
+  unsigned long long bad = 0;
+  for (unsigned long long b = 0x00800000ull + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b <= 0x7f7fffffull; b += (unsigned long long)gridDim.x * blockDim.x) {
+    const float x = __uint_as_float((unsigned)b);
+    bad += __float_as_uint(rsqrt_normal(x)) != __float_as_uint(rsqrtf(x));
+  }
+  if (bad) atomicAdd(mismatches, bad);
+}
+__global__ void selftest_outside_box(const SceneDev sc, unsigned long long* mismatches) {  // every non-NaN float on each axis
+  unsigned long long bad = 0;
+  for (unsigned long long b = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b <= 0xffffffffull; b += (unsigned long long)gridDim.x * blockDim.x) {
+    const float x = __uint_as_float((unsigned)b);
+    if (x != x) continue;
+    for (int k = 0; k < 3; k++) {
+      Photon p;
+      p.x = p.y = p.z = 0.5f * fminf(sc.bbox[0], fminf(sc.bbox[1], sc.bbox[2]));  // the other two axes inside
+      (k == 0 ? p.x : k == 1 ? p.y : p.z) = x;
+      bad += outside_box(sc, p) != (locate_voxel(sc, p) < 0);
+    }
+  }
+  if (bad) atomicAdd(mismatches, bad);
+}
+}  // namespace
+
+extern "C" int mcgpu_dev_selftest(struct mcgpu_device* d, const char* name, unsigned long long* mismatches, char* err, size_t errlen) {
+  CK(cudaSetDevice(d->ordinal));
+  unsigned long long* counter = NULL;
+  CK(cudaMalloc((void**)&counter, sizeof *counter));
+  CK(cudaMemset(counter, 0, sizeof *counter));
+  const int grid = d->sm_count * 8, block = 256;
+  if (!strcmp(name, "log_uniform"))
+    selftest_log_uniform<<<grid, block, 0, d->stream>>>(counter);
+  else if (!strcmp(name, "rsqrt_normal"))
+    selftest_rsqrt_normal<<<grid, block, 0, d->stream>>>(counter);
+  else if (!strcmp(name, "outside_box")) {
+    if (!d->d_image) {
+      cudaFree(counter);
+      snprintf(err, errlen, "selftest outside_box needs a loaded geometry");
+      return -1;
+    }
+    selftest_outside_box<<<grid, block, 0, d->stream>>>(d->scene, counter);
+  } else {
+    cudaFree(counter);
+    snprintf(err, errlen, "unknown self test '%s' (log_uniform, rsqrt_normal, outside_box)", name);
+    return -1;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(d->stream);
+  if (e == cudaSuccess) e = cudaMemcpy(mismatches, counter, sizeof *counter, cudaMemcpyDeviceToHost);
+  cudaFree(counter);
+  CK(e);
+  return 0;
+}
+#endif

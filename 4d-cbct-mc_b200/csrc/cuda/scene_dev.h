@@ -14,7 +14,7 @@ struct McgpuSceneDev {
   const float2* woodcock;         // [nE]
   const float4* ray_xpab;         // [num_slots][128] (xco, pco, aco, bco)
   const uchar2* ray_itl_itu;      // [num_slots][128]
-  const float4* cmp_shells;       // [num_slots][40] (fco, uico, fj0, -)
+  const float4* cmp_shells;       // [num_slots][40] (fco, uico, fj0, uico*510998.918f)
   const mcgpu_spectrum* spectrum; // global copy
   unsigned long long* image;      // [4][Npix]
   int cmp_noscco[MCGPU_MAX_MATERIALS];
@@ -28,6 +28,7 @@ struct McgpuSceneDev {
   int nvx, nvy, nvz;
   float inv_voxel[3];
   float bbox[3];
+  unsigned box_hi[3];  // bits(bbox[k] - EPS_SOURCE) - bits(EPS_SOURCE): right-hand sides of locate_voxel_fast's unsigned comparisons
   float e0, ide;
 };
 

@@ -175,9 +175,10 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
         }
       }
     }
-    q = __shfl_sync(MCGPU_FULL_MASK, q, 0);
-    n = __shfl_sync(MCGPU_FULL_MASK, n, 0);
-    pos = __shfl_sync(MCGPU_FULL_MASK, pos, 0);
+    {  // one broadcast: queue (2 bits), count (6 bits), ring position (the rings have at most 2048 entries)
+      const unsigned packed = __shfl_sync(MCGPU_FULL_MASK, (unsigned)q | ((unsigned)n << 2) | ((pos & (unsigned)ring_mask) << 8), 0);
+      q = (int)(packed & 3u), n = (int)((packed >> 2) & 63u), pos = packed >> 8;
+    }
     if (n <= 0) break;
 
     bool act = (int)lane < n;
@@ -230,15 +231,14 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
       const int thr = min(w_threshold, (n + 1) >> 1);
       do {
         if (state == ST_W) {
-          const float step = -(mfp_woodcock)*logf(rng.uniform());
+          const float step = -(mfp_woodcock)*log_uniform(rng.uniform());
           p.x += step * p.u;
           p.y += step * p.v;
           p.z += step * p.w;
-          const int absvox = locate_voxel(sc, p);
-          if (absvox < 0) {
+          if (outside_box(sc, p)) {
             state = ST_T;  // escaped with index > -1: goes to the detector
           } else {
-            const float2 md = fetch_voxel<BITS>(sc, sh_palette, absvox);
+            const float2 md = fetch_voxel<BITS>(sc, sh_palette, voxel_index(sc, p));
             slot = __float_as_int(md.y);
             if (slot != slot_old) {
               const float4* r4 = reinterpret_cast<const float4*>(&sc.mfp[(size_t)index * sc.num_slots + slot]);
@@ -369,11 +369,14 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
 
     // ------------------------------------------------------------------ store what every kind changes, hand the ids on
     if (act) {
-      PF(F_X) = p.x, PF(F_Y) = p.y, PF(F_Z) = p.z, PF(F_U) = p.u, PF(F_V) = p.v, PF(F_W) = p.w, PF(F_E) = p.E;
-      PF(F_S0) = s0;
-      PI(F_HIST) = hist_left;
+      PF(F_X) = p.x, PF(F_Y) = p.y, PF(F_Z) = p.z;
       PI(F_S1) = rng.s1, PI(F_S2) = rng.s2;
       PI(F_META) = wf_pack_meta(state, scatter_state, slot);
+      if (q != Q_W) {  // a tracking batch moves the photon and draws random numbers; direction, energy, S0 and the history count stay
+        PF(F_U) = p.u, PF(F_V) = p.v, PF(F_W) = p.w, PF(F_E) = p.E;
+        PF(F_S0) = s0;
+        PI(F_HIST) = hist_left;
+      }
     }
     __threadfence_block();
     const int nq = !act || state == ST_F ? -1 : state == ST_W ? Q_W : (state == ST_C || state == ST_CT) ? Q_C : state == ST_R ? Q_R : Q_N;

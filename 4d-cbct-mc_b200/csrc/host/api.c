@@ -76,6 +76,7 @@ int mcgpu_load_input(mcgpu_ctx* ctx, const char* in_path) {
   if ((rc = mcgpu_read_spectrum(ctx, ctx->in.file_espc)) != MCGPU_OK) return rc;
   if ((rc = mcgpu_build_views(ctx)) != MCGPU_OK) return rc;
   ctx->hpt_current = ctx->in.histories_per_thread;
+  ctx->hist_current = 0;
   ctx->have_input = 1;
   return MCGPU_OK;
 }
@@ -114,6 +115,7 @@ int mcgpu_set_histories(mcgpu_ctx* ctx, unsigned long long total_histories) {
   if (!ctx || !ctx->have_input) return MCGPU_E_STATE;
   ctx->in.total_histories = total_histories;
   ctx->hpt_current = ctx->in.histories_per_thread;
+  ctx->hist_current = 0;
   return MCGPU_OK;
 }
 
@@ -136,17 +138,26 @@ static int projection_skipped(const mcgpu_ctx* ctx, int p) { /* H:671-677, Q6 */
   return (a < ctx->in.angularROI_0) || (a > ctx->in.angularROI_1);
 }
 
-/* Seed, histories/thread and grid the reference's loop reaches projection p with (Q1). */
+/* Seed, histories/thread and grid the reference's loop reaches projection p with (Q1).  Both inputs of the grid rule are
+ * sticky across projections: histories_per_thread (H:833) and the history count itself, which the reference overwrites
+ * with the launched count (H:841) -- so after a >65535-block correction every later projection runs 65000 blocks too. */
 static void schedule_for(const mcgpu_ctx* ctx, int p, int* seed, int* hpt, int* blocks, unsigned long long* launched) {
+  unsigned long long hist = ctx->in.total_histories;
   int q;
   *seed = ctx->in.seed_input;
   *hpt = ctx->in.histories_per_thread;
   for (q = 0;; q++) {
     if (q < p && projection_skipped(ctx, q)) continue;
-    mcgpu_grid_rule(ctx->in.total_histories, ctx->in.threads_per_block, hpt, blocks, launched);
+    mcgpu_grid_rule(hist, ctx->in.threads_per_block, hpt, blocks, launched);
+    hist = *launched;
     if (q >= p) break;
     *seed = mcgpu_ranecu_advance_projection_seed(*seed, *launched);
   }
+}
+
+void mcgpu_current_grid(const mcgpu_ctx* ctx, int* hpt, int* blocks, unsigned long long* launched) {
+  *hpt = ctx->hpt_current ? ctx->hpt_current : ctx->in.histories_per_thread;
+  mcgpu_grid_rule(ctx->hist_current ? ctx->hist_current : ctx->in.total_histories, ctx->in.threads_per_block, hpt, blocks, launched);
 }
 
 int mcgpu_projection_seed(mcgpu_ctx* ctx, int p, int* seed_out) {
@@ -185,6 +196,7 @@ int mcgpu_run_streams(mcgpu_ctx* ctx, int p, long long stream_begin, long long s
   if ((rc = ready_to_run(ctx, p)) != MCGPU_OK) return rc;
   schedule_for(ctx, p, &seed, &hpt, &blocks, &launched);
   ctx->hpt_current = hpt;
+  ctx->hist_current = launched;
   if (stream_begin < 0 || stream_end > (long long)blocks * ctx->in.threads_per_block || stream_begin > stream_end)
     return mcgpu_fail(ctx, MCGPU_E_ARG, "run_streams: stream range [%lld,%lld) outside [0,%lld)", stream_begin, stream_end, (long long)blocks * ctx->in.threads_per_block);
   if ((rc = launch_on(ctx, 0, p, stream_begin, stream_end, seed, hpt)) != MCGPU_OK) return rc;
@@ -201,6 +213,7 @@ int mcgpu_run_projection(mcgpu_ctx* ctx, int p, uint64_t* image_host) {
   if ((rc = ready_to_run(ctx, p)) != MCGPU_OK) return rc;
   schedule_for(ctx, p, &seed, &hpt, &blocks, &launched);
   ctx->hpt_current = hpt;
+  ctx->hist_current = launched;
   n = ctx->num_devices;
   if (n > blocks) n = blocks;
   /* history split: contiguous block ranges of the reference grid, one per device */
@@ -237,6 +250,12 @@ void* mcgpu_device_image(mcgpu_ctx* ctx) { return (ctx && ctx->num_devices > 0) 
 double mcgpu_last_kernel_ms(const mcgpu_ctx* ctx) { return ctx ? ctx->last_kernel_ms : 0.0; }
 double mcgpu_last_reduce_ms(const mcgpu_ctx* ctx) { return ctx ? ctx->last_reduce_ms : 0.0; }
 const char* mcgpu_reduce_kind(const mcgpu_ctx* ctx) { return ctx ? mcgpu_dev_reducer_kind(ctx->reducer) : "none"; }
+int mcgpu_device_selftest(mcgpu_ctx* ctx, const char* name, unsigned long long* mismatches) {
+  if (!ctx || !name || !mismatches) return MCGPU_E_ARG;
+  if (ctx->num_devices < 1) return mcgpu_fail(ctx, MCGPU_E_CUDA, "selftest: no usable CUDA device");
+  return mcgpu_dev_selftest(ctx->dev[0], name, mismatches, ctx->err, sizeof ctx->err) == 0 ? MCGPU_OK : MCGPU_E_CUDA;
+}
+
 int mcgpu_get_scan_stats(const mcgpu_ctx* ctx, double* out, int n) {
   int k;
   if (!ctx || !out) return MCGPU_E_ARG;
@@ -405,17 +424,19 @@ int mcgpu_run_all(mcgpu_ctx* ctx, mcgpu_progress_cb cb, void* user) {
     seed = ctx->in.seed_input;
     hpt = ctx->in.histories_per_thread;
     blocks = 1;
+    launched = ctx->in.total_histories;
     for (p = 0; p < P; p++) {
       if (projection_skipped(ctx, p)) continue;
-      mcgpu_grid_rule(ctx->in.total_histories, ctx->in.threads_per_block, &hpt, &blocks, &launched);
+      mcgpu_grid_rule(launched, ctx->in.threads_per_block, &hpt, &blocks, &launched); /* sticky hpt (H:833) and history count (H:841) */
       sh.seeds[p] = seed;
       seed = mcgpu_ranecu_advance_projection_seed(seed, launched);
     }
-    /* the sticky histories/thread only changes at the first simulated projection; using the
-     * final value for all of them is what the reference's loop does too (H:833) */
+    /* hpt and the history count only change at the first simulated projection (the rule is idempotent afterwards),
+     * so every projection of the scan runs the same grid */
     sh.hpt = hpt;
     sh.blocks = blocks;
     ctx->hpt_current = hpt;
+    ctx->hist_current = launched;
     pthread_mutex_init(&sh.mu, NULL);
     pthread_cond_init(&sh.cv, NULL);
     ctx->verbose = 0; /* per-projection report banners would interleave across workers */
@@ -483,8 +504,7 @@ int mcgpu_get_info(const mcgpu_ctx* ctx, mcgpu_info* out) {
   out->fast_math = ctx->fast_math;
   if (ctx->have_input) {
     const mcgpu_view* v = &ctx->views[0];
-    hpt = ctx->hpt_current ? ctx->hpt_current : ctx->in.histories_per_thread;
-    mcgpu_grid_rule(ctx->in.total_histories, ctx->in.threads_per_block, &hpt, &blocks, &launched);
+    mcgpu_current_grid(ctx, &hpt, &blocks, &launched);
     out->num_projections = ctx->in.num_projections;
     out->num_pixels_x = v->num_pixels_x;
     out->num_pixels_z = v->num_pixels_z;

@@ -11,9 +11,9 @@
 #define SCALE_eV 100.0f
 
 static unsigned long long launched_per_projection(mcgpu_ctx* ctx) {
-  int hpt = ctx->hpt_current ? ctx->hpt_current : ctx->in.histories_per_thread, blocks;
+  int hpt, blocks;
   unsigned long long launched;
-  mcgpu_grid_rule(ctx->in.total_histories, ctx->in.threads_per_block, &hpt, &blocks, &launched);
+  mcgpu_current_grid(ctx, &hpt, &blocks, &launched);
   return launched;
 }
 

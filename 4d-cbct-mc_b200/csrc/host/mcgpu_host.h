@@ -117,7 +117,7 @@ typedef struct mcgpu_scene {
   mcgpu_f2* woodcock;     /* [nE] */
   float* ray_xpab;        /* [num_slots][128][4] = xco, pco, aco, bco */
   uint8_t* ray_itl_itu;   /* [num_slots][128][2] */
-  float* cmp_shells;      /* [num_slots][40][4] = fco, uico, fj0, 0 */
+  float* cmp_shells;      /* [num_slots][40][4] = fco, uico, fj0, uico*510998.918f */
   int cmp_noscco[MCGPU_MAX_MATERIALS]; /* per slot */
   /* palette remapped to slots */
   int palette_size, voxel_bits;
@@ -142,6 +142,8 @@ struct mcgpu_ctx {
   mcgpu_scene scene;
   /* launch state */
   int hpt_current;   /* sticky histories_per_thread (H:833) */
+  unsigned long long hist_current; /* sticky history count: the reference overwrites total_histories with the launched count (H:841),
+                                      which the NEXT projection's grid rule starts from; 0 = the .in value */
   int num_devices;
   struct mcgpu_device** dev;
   double last_kernel_ms;
@@ -164,6 +166,8 @@ void mcgpu_free_volume(mcgpu_volume* v);
 void mcgpu_free_tables(mcgpu_tables* t);
 void mcgpu_free_scene(mcgpu_scene* s);
 int mcgpu_fail(mcgpu_ctx* ctx, int code, const char* fmt, ...);
+/* grid of the projection(s) simulated last (or of the first one before any run): sticky hpt AND sticky history count */
+void mcgpu_current_grid(const mcgpu_ctx* ctx, int* hpt, int* blocks, unsigned long long* launched);
 char* mcgpu_fgets_trimmed(char* out, int num, FILE* f);
 void mcgpu_trim_name(const char* line, char* name);
 
@@ -193,6 +197,8 @@ void mcgpu_dev_reducer_free(struct mcgpu_reducer* r);
 const char* mcgpu_dev_reducer_kind(const struct mcgpu_reducer* r);
 int mcgpu_dev_reduce(struct mcgpu_reducer* r, float* reduce_ms, char* err, size_t errlen);
 void* mcgpu_dev_image_ptr(struct mcgpu_device* d);
+/* exhaustive device checks of the kernel's arithmetic shortcuts against the CUDA functions they replace (launch.cu) */
+int mcgpu_dev_selftest(struct mcgpu_device* d, const char* name, unsigned long long* mismatches, char* err, size_t errlen);
 /* pipelined scan: launch projection work into image slot 0/1 (asynchronous; the copy to a pinned host buffer is queued behind
  * it on a second stream), wait for a slot's copy (kernel_ms = device time of its kernel, *host = the pinned buffer) */
 int mcgpu_dev_pipeline_begin(struct mcgpu_device* d, char* err, size_t errlen);

@@ -106,8 +106,7 @@ int mcgpu_write_projection_ascii(mcgpu_ctx* ctx, int p, const uint64_t* image, d
   if (!ctx || !ctx->have_input || !image || p < 0 || p >= ctx->in.num_projections) return MCGPU_E_ARG;
   v0 = &ctx->views[0];
   vp = &ctx->views[p];
-  hpt = ctx->hpt_current ? ctx->hpt_current : ctx->in.histories_per_thread;
-  mcgpu_grid_rule(ctx->in.total_histories, ctx->in.threads_per_block, &hpt, &blocks, &launched);
+  mcgpu_current_grid(ctx, &hpt, &blocks, &launched);
   total_histories = launched;
   projection_angles(ctx, p, &cur, &seq);
   snprintf(name, sizeof name, "%s_%010.6fdeg", ctx->in.file_output, seq);
@@ -216,8 +215,7 @@ int mcgpu_write_projection_raw(mcgpu_ctx* ctx, int p, const uint64_t* image) {
   float* buf;
   FILE* f;
   if (!ctx || !ctx->have_input || !image || p < 0 || p >= ctx->in.num_projections) return MCGPU_E_ARG;
-  hpt = ctx->hpt_current ? ctx->hpt_current : ctx->in.histories_per_thread;
-  mcgpu_grid_rule(ctx->in.total_histories, ctx->in.threads_per_block, &hpt, &blocks, &launched);
+  mcgpu_current_grid(ctx, &hpt, &blocks, &launched);
   projection_angles(ctx, p, &cur, &seq);
   snprintf(name, sizeof name, "%s_%010.6fdeg.raw", ctx->in.file_output, seq);
   n = (size_t)4 * ctx->views[0].total_num_pixels;

@@ -414,6 +414,7 @@ int mcgpu_build_scene(mcgpu_ctx* ctx) {
       d[0] = t->cmp_fco[m + i * MCGPU_MAX_MATERIALS];
       d[1] = t->cmp_uico[m + i * MCGPU_MAX_MATERIALS];
       d[2] = t->cmp_fj0[m + i * MCGPU_MAX_MATERIALS];
+      d[3] = d[1] * 510998.918f; /* U * m_e c^2 [eV] of K:1329/1369, the float product the kernel would form per shell term */
     }
   }
   s->tally_material_dose = ctx->have_input && ctx->in.flag_material_dose == 1;

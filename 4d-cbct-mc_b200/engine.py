@@ -54,6 +54,7 @@ _SIGS = {
     "mcgpu_last_reduce_ms": (C.c_double, [C.c_void_p]),
     "mcgpu_reduce_kind": (C.c_char_p, [C.c_void_p]),
     "mcgpu_get_scan_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_int]),
+    "mcgpu_device_selftest": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_ulonglong)]),
     "mcgpu_run_all": (C.c_int, [C.c_void_p, PROGRESS_CB, C.c_void_p]),
     "mcgpu_write_projection_ascii": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_double]),
     "mcgpu_write_projection_raw": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
@@ -222,6 +223,12 @@ class Engine:
     @property
     def reduce_kind(self) -> str:
         return (_lib.mcgpu_reduce_kind(self._h) or b"none").decode()
+
+    def selftest(self, name: str) -> int:
+        """Mismatches of a device self test (include/mcgpu_b200.h: mcgpu_device_selftest); 0 = the shortcut is exact."""
+        n = C.c_ulonglong(1)
+        self._check(_lib.mcgpu_device_selftest(self._h, name.encode(), C.byref(n)))
+        return int(n.value)
 
     def scan_stats(self) -> dict:
         out = (C.c_double * 6)()

@@ -199,6 +199,14 @@ int mcgpu_projection_seed(mcgpu_ctx* ctx, int p, int* seed_out);
  * Returns bytes copied (<= cap) or a negative error; out==NULL returns the size. */
 long long mcgpu_copy_table(const mcgpu_ctx* ctx, const char* name, void* out, size_t cap);
 
+/* Exhaustive device-side checks of the arithmetic shortcuts the transport kernel takes inside the reference's expressions,
+ * each against the CUDA function it replaces, bit for bit over its whole domain; *mismatches must come back 0:
+ *   "log_uniform"  logf without its special-case branches, on every value RANECU can return (K:965-1015 -> K:251)
+ *   "rsqrt_normal" rsqrtf without its subnormal scaling, on every positive normal float (K:1329, K:1369)
+ *   "outside_box"  locate_voxel's six float comparisons (K:1033-1045) as three unsigned ones, on every non-NaN float per
+ *                  axis of the loaded geometry (needs load_voxels + load_materials first) */
+int mcgpu_device_selftest(mcgpu_ctx* ctx, const char* name, unsigned long long* mismatches);
+
 /* RANECU helpers exposed for known-answer tests (K:841-894, K:965-986, H:3456-3485). */
 void mcgpu_ranecu_init_stream(long long stream, int histories_per_thread, int seed_input, int* s1, int* s2);
 float mcgpu_ranecu_next(int* s1, int* s2);

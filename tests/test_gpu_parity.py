@@ -47,6 +47,16 @@ def test_bit_exact_against_reference_cuda_source(pkg, oracle_py, gpu_engine_fact
     eng.close()
 
 
+@pytest.mark.parametrize("name", ["log_uniform", "rsqrt_normal", "outside_box"])
+def test_arithmetic_shortcuts_are_exact_on_their_whole_domain(pkg, gpu_engine_factory, cases, name):
+    """The kernel evaluates logf / rsqrtf / the bounding-box test of the reference with fewer instructions (transport.cuh:
+    log_uniform, rsqrt_normal, outside_box); each is compared on the device with the function it replaces for EVERY input it
+    can see (all 2 147 483 562 RANECU outputs, all positive normal floats, all non-NaN floats per axis)."""
+    eng = gpu_engine_factory(cases["thorax_oblique"][0])
+    assert eng.selftest(name) == 0
+    eng.close()
+
+
 @pytest.mark.parametrize("bits", ["8", "16", "64"])
 def test_every_voxel_packing_gives_the_same_tallies(pkg, gpu_engine_factory, cases, bits, monkeypatch):
     inp, cfg, _ = cases["thorax_p4"]

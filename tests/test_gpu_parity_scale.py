@@ -104,7 +104,7 @@ def test_patient_material_set_40_and_36_shells(pkg, oracle_py, gpu_engine_factor
 def test_more_than_65535_blocks_rule_is_sticky_on_the_device(pkg, oracle_py, gpu_engine_factory, tmp_path):
     ph = pkg.phantoms.thorax(shape=(64, 64, 25), spacing_mm=8.0)
     info, ms, t_ref, log = compare_with_reference_cuda(pkg, oracle_py, gpu_engine_factory, tmp_path, ph, n_histories=3_000_000, threads_per_block=32,
-                                                       histories_per_thread=1, n_projections=2, angle_between_projections=90.0, n_detector_pixels=(231, 96))
+                                                       histories_per_thread=1, n_projections=2, angle_between_projections=90.0, n_detector_pixels=(924, 384))
     assert info.num_blocks == 65_000 and info.histories_per_thread == 2 and info.launched_histories == 65_000 * 32 * 2
     assert "65000" in log
     assert t_ref < 60

@@ -80,3 +80,24 @@ def test_grid_rule_above_65535_blocks_is_sticky(pkg, cases, tmp_path):
         blocks, hpt, launched = pkg.mcio.launched_histories(n, 128, 150)
         assert (info.num_blocks, info.histories_per_thread, info.launched_histories) == (blocks, hpt, launched) == (65000, 1431, 11_905_920_000)
         assert len({eng.projection_seed(p) for p in range(3)}) == 3
+
+
+def test_history_count_is_sticky_too_after_the_65535_block_correction(pkg, oracle_py, cases, tmp_path):
+    """H:841 overwrites total_histories with the launched count, and the NEXT projection's grid rule starts from it: at the
+    reference count, projection 2 runs 65000 blocks of 1431 histories per thread again (11 905 920 000 histories) -- not the
+    64 986 blocks the .in value (11 903 320 312) would give with the sticky 1431.  Visible on the host through the seed
+    schedule (each projection advances the seed by the histories launched before it) and through the oracle."""
+    n = 11_903_320_312
+    inp, _ = make(pkg, cases, tmp_path, n_histories=n, n_projections=3, angle_between_projections=1.0)
+    with pkg.engine.Engine() as eng:
+        eng.load_input(inp)
+        s0 = eng.projection_seed(0)
+        s1 = pkg.engine.advance_projection_seed(s0, 11_905_920_000)
+        s2 = pkg.engine.advance_projection_seed(s1, 11_905_920_000)
+        assert (eng.projection_seed(1), eng.projection_seed(2)) == (s1, s2)
+        assert s2 != pkg.engine.advance_projection_seed(s1, 64_986 * 128 * 1431)
+    # small case, through the oracle's GPU-rule schedule: 32 threads/block, 1 history/thread, 3e6 histories
+    inp, _ = make(pkg, cases, tmp_path, n_histories=3_000_000, n_projections=2, angle_between_projections=90.0, threads_per_block=32, histories_per_thread=1)
+    ora = oracle_py.Oracle(inp, cxx_host_math=True)
+    _, launched = ora.run_gpu_rule(1, threads=8)
+    assert launched == 65_000 * 32 * 2

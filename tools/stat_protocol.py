@@ -1,0 +1,157 @@
+#!/usr/bin/env python3
+"""Statistical parity at north_star scale (GPU box; not a pytest: ~5 minutes of CPU + GPU work).
+
+BASELINE.json: "per-pixel means must agree within statistical uncertainty (|z|<3 on >=99.7% of pixels, mean relative
+difference <0.5% at 1e9 histories)" whenever the two programs do not follow the same random-number streams.  Two pairs:
+
+  A. this engine, exact arithmetic        vs  the CPU oracle (bit-exact port of the reference's CPU build), independent seeds
+  B. this engine, fast-math arithmetic    vs  the reference's CUDA source with its shipped fast-math flags
+                                              (oracle/_ref/MC-GPU_v1.3_sm100_fast.x), independent seeds
+
+K seeds x N histories per side (default 16 x 1e8 = 1.6e9 histories per side), thorax phantom 128x128x50 @ 4 mm, one rotated
+projection, 231x96 detector (8x8 binned default panel, so that a pixel sees thousands of histories).  Per scatter plane
+(non-scattered, Compton, Rayleigh, multiple) and for the total image:
+
+  z        (mean_a - mean_b) / sqrt(var_a/K + var_b/K), variances estimated per pixel from the K seeds.  With only 2K-2 ~ 30
+           degrees of freedom this is Student-t distributed: |t_30| < 3 holds for 99.46 % of pixels under the null hypothesis,
+           not 99.73 %; both numbers are reported next to the observed fraction.
+  z_pooled the same with the variances averaged over the 3x3 neighbourhood of the pixel (neighbouring pixels have the same
+           variance to within a per cent), ~270 degrees of freedom: the normal 99.7 % criterion applies to this one.
+  rel      relative difference of the plane sums (the "mean relative difference").
+
+Usage: python tools/stat_protocol.py [--seeds 16] [--histories 100000000] [--out gpurun_out/r02_stat_protocol.json]"""
+import argparse
+import json
+import os
+import re
+import shutil
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "oracle"))
+from __graft_entry__ import import_package  # noqa: E402
+
+pkg = import_package()
+import oracle_py  # noqa: E402
+
+N_PIX = (231, 96)
+
+
+def box3(a):
+    """mean over the 3x3 neighbourhood (edges: the neighbours that exist)"""
+    p = np.pad(a, ((0, 0), (1, 1), (1, 1)), mode="edge")
+    return sum(p[:, i:i + a.shape[1], j:j + a.shape[2]] for i in range(3) for j in range(3)) / 9.0
+
+
+def compare(a, b, label):
+    """a, b: float64 [K, 4, Nz, Nx] tallies of the two programs"""
+    K = a.shape[0]
+    out = {"label": label, "seeds_per_side": K}
+    planes = {"non_scattered": 0, "compton": 1, "rayleigh": 2, "multiple": 3, "total": None}
+    for name, k in planes.items():
+        x = a.sum(axis=1) if k is None else a[:, k]
+        y = b.sum(axis=1) if k is None else b[:, k]
+        mx, my = x.mean(0), y.mean(0)
+        vx, vy = x.var(0, ddof=1), y.var(0, ddof=1)
+        sem = np.sqrt(vx / K + vy / K)
+        sem_p = np.sqrt(box3(vx[None])[0] / K + box3(vy[None])[0] / K)
+        lit = (mx > 0) & (my > 0) & (sem > 0)
+        z = (mx[lit] - my[lit]) / sem[lit]
+        zp = (mx[lit] - my[lit]) / sem_p[lit]
+        out[name] = {
+            "pixels_compared": int(lit.sum()), "frac_abs_z_lt_3": float(np.mean(np.abs(z) < 3)), "frac_abs_z_pooled_lt_3": float(np.mean(np.abs(zp) < 3)),
+            "z_mean": float(z.mean()), "z_std": float(z.std()), "z_pooled_std": float(zp.std()),
+            "rel_diff_of_plane_sum": float((mx.sum() - my.sum()) / my.sum()),
+            "sem_of_rel_diff": float(np.sqrt(x.sum(axis=(1, 2)).var(ddof=1) / K + y.sum(axis=(1, 2)).var(ddof=1) / K) / my.sum()),
+        }
+    t = out["total"]
+    out["pass_z_pooled_997"] = bool(all(out[n]["frac_abs_z_pooled_lt_3"] >= 0.997 - 3 * np.sqrt(0.003 * 0.997 / max(out[n]["pixels_compared"], 1)) for n in planes))
+    out["pass_mean_rel_diff_0p5pct"] = bool(all(abs(out[n]["rel_diff_of_plane_sum"]) < 5e-3 for n in planes))
+    out["expected_frac_under_null"] = {"student_t_2K-2": 0.9946 if K == 16 else None, "normal": 0.9973}
+    print(label, "total: |z|<3", t["frac_abs_z_lt_3"], "pooled", t["frac_abs_z_pooled_lt_3"], "rel", t["rel_diff_of_plane_sum"], flush=True)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seeds", type=int, default=16)
+    ap.add_argument("--histories", type=int, default=100_000_000)
+    ap.add_argument("--out", default=str(ROOT / "gpurun_out" / "r02_stat_protocol.json"))
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    K, N = args.seeds, args.histories
+    tmp = Path(tempfile.mkdtemp(prefix="mcgpu_stat_"))
+    ph = pkg.phantoms.thorax(shape=(128, 128, 50), spacing_mm=4.0)
+    vox = pkg.mcio.write_vox(tmp / "geometry.vox.gz", ph.materials, ph.densities, ph.spacing_cm)
+    base = dict(n_histories=N, n_detector_pixels=N_PIX, n_projections=2, angle_between_projections=63.0, source_position=pkg.mcio.default_source_position(ph.size_mm))
+    inp = pkg.mcio.write_input(pkg.mcio.ScanConfig(**base), vox, tmp, tmp / "input.in")
+    P = 1  # the rotated pose
+    report = {"phantom": "thorax 128x128x50 @ 4 mm, 6 materials", "detector": list(N_PIX), "projection": P, "seeds_per_side": K, "histories_per_seed": N,
+              "histories_per_side": K * N}
+
+    eng = pkg.engine.Engine([0])
+    eng.load_input(inp).load_voxels().load_materials()
+    launched = int(eng.info.launched_histories)
+    report["launched_per_seed"] = launched
+    ours = {}
+    for fast in (False, True):
+        eng.set_fast_math(fast)
+        t0 = time.time()
+        imgs = []
+        for k in range(K):
+            eng.set_seed((3000 if fast else 1000) + k)
+            imgs.append(eng.run_projection(P).astype(np.float64))
+        ours["fast" if fast else "exact"] = np.array(imgs)
+        report[f"ours_{'fast' if fast else 'exact'}_seconds"] = time.time() - t0
+    eng.close()
+
+    # ---- B: the reference CUDA source with its shipped flags, seeds 5000 + 17 k, one process per seed (it writes ASCII projections)
+    assert oracle_py.REF_CUDA_FAST.exists(), "oracle/_ref/MC-GPU_v1.3_sm100_fast.x is missing"
+    det_cm = (71.7024, 29.7984)
+    ref = []
+    t0 = time.time()
+    for k in range(K):
+        sub = tmp / f"ref{k}"
+        cfg = pkg.mcio.ScanConfig(random_seed=5000 + 17 * k, **base)
+        rin = pkg.mcio.write_input(cfg, vox, sub, sub / "input.in")
+        log = oracle_py.run_reference_binary(oracle_py.REF_CUDA_FAST, rin, cwd=sub)
+        m = re.findall(r"(\d+) histories in total", log)
+        assert m and int(m[0]) == launched, (m, launched)
+        name = Path(pkg.mcio.projection_filename("projection", P * 63.0)).name
+        vals = pkg.mcio.read_projection(sub / name, N_PIX)
+        norm = (1.0 / 100.0) * float(np.float32(N_PIX[0]) / np.float32(det_cm[0])) * float(np.float32(N_PIX[1]) / np.float32(det_cm[1])) / float(launched)
+        ref.append(vals / norm)  # back to tally units (sum of E*100); the 1e-8 print resolution is far below one count here? checked below
+        shutil.rmtree(sub, ignore_errors=True)
+    report["reference_fast_seconds"] = time.time() - t0
+    report["reference_print_resolution_in_counts"] = 1e-8 / norm
+    ref = np.array(ref)
+    report["B_ours_fast_vs_reference_cuda_fast"] = compare(ours["fast"], ref, "B: ours fast-math vs reference CUDA (shipped fast-math flags)")
+    report["C_ours_exact_vs_ours_fast"] = compare(ours["exact"], ours["fast"], "C: ours exact (seeds 1000+k) vs ours fast-math (seeds 3000+k)")
+
+    # ---- A: the CPU oracle (reference CPU build restated, bit-exact with it on the golden vectors), seeds 5000 + 17 k
+    if not args.skip_cpu:
+        cores = os.cpu_count() or 1
+        ora = oracle_py.Oracle(inp, cxx_host_math=True)
+        t0 = time.time()
+        cpu = []
+        batches = int(np.ceil(launched / 150))
+        for k in range(K):
+            cpu.append(ora.run_batches(P, 5000 + 17 * k, 150, 0, batches, threads=cores).astype(np.float64))
+            print(f"oracle seed {k + 1}/{K}: {time.time() - t0:.0f} s", flush=True)
+        report["oracle_seconds"], report["oracle_threads"] = time.time() - t0, cores
+        report["A_ours_exact_vs_cpu_oracle"] = compare(ours["exact"], np.array(cpu), "A: ours exact vs CPU oracle")
+    Path(args.out).parent.mkdir(parents=True, exist_ok=True)
+    Path(args.out).write_text(json.dumps(report, indent=1))
+    shutil.rmtree(tmp, ignore_errors=True)
+    print(json.dumps({k: v for k, v in report.items() if not isinstance(v, dict)}, indent=1))
+
+
+if __name__ == "__main__":
+    main()
