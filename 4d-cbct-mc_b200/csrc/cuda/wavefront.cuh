@@ -61,7 +61,7 @@ struct WfLayout {
 // (>= the pool, which is at most 2 contexts per thread; a power of two)
 __host__ __device__ inline WfLayout wavefront_layout(int num_slots, int max_shells, int palette_entries, int pool_size, int warps, int rows) {
   WfLayout L;
-  L.stride = regroup_scratch_stride(max_shells);
+  L.stride = wavefront_scratch_stride(max_shells);
   L.ring = warps <= 16 ? 1024 : 2048;
   L.shells = (sizeof(SharedTables) + 15) & ~size_t(15);
   L.scratch = L.shells + sizeof(float4) * num_slots * MCGPU_MAX_SHELLS;

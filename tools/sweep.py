@@ -26,7 +26,8 @@ def main():
     kernels = [int(x) for x in opts.get("kernels", "1,2").split(",")]
     workloads = args or ["thorax", "catphan"]
     factories = {"thorax": pkg.phantoms.thorax, "catphan": pkg.phantoms.catphan604, "water": pkg.phantoms.water_cylinder,
-                 "air": pkg.phantoms.air_scan, "linepairs": pkg.phantoms.line_pairs}
+                 "air": pkg.phantoms.air_scan, "linepairs": pkg.phantoms.line_pairs, "patient": pkg.phantoms.patient}
+    bits_list = opts.get("bits", "0").split(",")  # voxel packing: 0 = the engine's choice, 8 / 16 / 64 force a wider one (MCGPU_VOXEL_BITS)
     out = {}
     for wl in workloads:
         ph = factories[wl]()
@@ -43,8 +44,13 @@ def main():
                 configs += [(k, t) for t in thresholds]
             else:
                 configs += [(k, t) for t in t3]
-        for k, t in configs:
+        configs = [(k, t, b) for (k, t) in configs for b in bits_list]
+        for k, t, bits in configs:
             os.environ["MCGPU_KERNEL"] = str(k)
+            if bits != "0":
+                os.environ["MCGPU_VOXEL_BITS"] = bits
+            else:
+                os.environ.pop("MCGPU_VOXEL_BITS", None)
             if k != 1:
                 os.environ["MCGPU_W_THRESHOLD"] = t.split(":")[0]
                 os.environ["MCGPU_WF_BLOCK"] = t.split(":")[1] if ":" in t else "512"
@@ -65,8 +71,8 @@ def main():
             if base is None:
                 base = img
             rate = info.launched_histories / (min(ms) / 1e3)
-            out[f"{wl}/k{k}/t{t}"] = {"hist_per_s": rate, "ms": min(ms), "identical_to_first": same}
-            print(f"{wl:10s} kernel v{k} cfg {t:>14s}: {rate:.4g} hist/s ({min(ms):.1f} ms) identical={same}", flush=True)
+            out[f"{wl}/k{k}/t{t}/bits{info.voxel_bits}"] = {"hist_per_s": rate, "ms": min(ms), "identical_to_first": same}
+            print(f"{wl:10s} kernel v{k} cfg {t:>14s} voxel bits {info.voxel_bits:2d}: {rate:.4g} hist/s ({min(ms):.1f} ms) identical={same}", flush=True)
             eng.close()
     (ROOT / "gpurun_out").mkdir(exist_ok=True)
     (ROOT / "gpurun_out" / "sweep.json").write_text(json.dumps(out, indent=1))
