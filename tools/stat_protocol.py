@@ -99,6 +99,7 @@ def main():
     eng = pkg.engine.Engine([0])
     eng.load_input(inp).load_voxels().load_materials()
     launched = int(eng.info.launched_histories)
+    proj_name = Path(eng.projection_filename(P)).name  # '<base>_<sequential angle>deg', the angle counted from the initial source direction
     report["launched_per_seed"] = launched
     ours = {}
     for fast in (False, True):
@@ -124,8 +125,7 @@ def main():
         log = oracle_py.run_reference_binary(oracle_py.REF_CUDA_FAST, rin, cwd=sub)
         m = re.findall(r"(\d+) histories in total", log)
         assert m and int(m[0]) == launched, (m, launched)
-        name = Path(pkg.mcio.projection_filename("projection", P * 63.0)).name
-        vals = pkg.mcio.read_projection(sub / name, N_PIX)
+        vals = pkg.mcio.read_projection(sub / proj_name, N_PIX)
         norm = (1.0 / 100.0) * float(np.float32(N_PIX[0]) / np.float32(det_cm[0])) * float(np.float32(N_PIX[1]) / np.float32(det_cm[1])) / float(launched)
         ref.append(vals / norm)  # back to tally units (sum of E*100); the 1e-8 print resolution is far below one count here? checked below
         shutil.rmtree(sub, ignore_errors=True)
