@@ -19,6 +19,33 @@ static double now_s(void) {
   return ts.tv_sec + 1e-9 * ts.tv_nsec;
 }
 
+typedef struct open_job {
+  int ordinal, threaded;
+  pthread_t thread;
+  struct mcgpu_device* dev;
+  char err[256];
+} open_job;
+
+static void* open_main(void* arg) {
+  open_job* j = (open_job*)arg;
+  j->dev = mcgpu_dev_open(j->ordinal, j->err, sizeof j->err);
+  return NULL;
+}
+
+typedef struct upload_job {
+  mcgpu_ctx* ctx;
+  int device, threaded, rc;
+  pthread_t thread;
+  char err[512];
+} upload_job;
+
+static void* upload_main(void* arg) {
+  upload_job* j = (upload_job*)arg;
+  mcgpu_ctx* ctx = j->ctx;
+  j->rc = mcgpu_dev_upload(ctx->dev[j->device], &ctx->scene, &ctx->vol, &ctx->spc, ctx->views[0].total_num_pixels, j->err, sizeof j->err);
+  return NULL;
+}
+
 mcgpu_ctx* mcgpu_create(const int* device_ids, int n_devices) {
   mcgpu_ctx* ctx = (mcgpu_ctx*)calloc(1, sizeof *ctx);
   int visible, i;
@@ -34,13 +61,33 @@ mcgpu_ctx* mcgpu_create(const int* device_ids, int n_devices) {
     free(ctx);
     return NULL;
   }
-  for (i = 0; i < n_devices; i++) {
-    int id = device_ids ? device_ids[i] : i, k, dup = 0;
-    if (id < 0 || id >= visible) id = ctx->num_devices % visible; /* Q13: out-of-range id -> use what is visible */
-    for (k = 0; k < ctx->num_devices; k++) dup |= (mcgpu_dev_ordinal(ctx->dev[k]) == id);
-    if (dup) continue;
-    ctx->dev[ctx->num_devices] = mcgpu_dev_open(id, ctx->err, sizeof ctx->err);
-    if (ctx->dev[ctx->num_devices]) ctx->num_devices++;
+  { /* CUDA context creation costs ~0.5 s per device: open the devices concurrently (one short-lived thread each) */
+    open_job* jobs = (open_job*)calloc((size_t)n_devices, sizeof *jobs);
+    int n_jobs = 0;
+    if (!jobs) {
+      free(ctx->dev);
+      free(ctx);
+      return NULL;
+    }
+    for (i = 0; i < n_devices; i++) {
+      int id = device_ids ? device_ids[i] : i, k, dup = 0;
+      if (id < 0 || id >= visible) id = n_jobs % visible; /* Q13: out-of-range id -> use what is visible */
+      for (k = 0; k < n_jobs; k++) dup |= (jobs[k].ordinal == id);
+      if (dup) continue;
+      jobs[n_jobs++].ordinal = id;
+    }
+    for (i = 0; i < n_jobs; i++) jobs[i].threaded = n_jobs > 1 && pthread_create(&jobs[i].thread, NULL, open_main, &jobs[i]) == 0;
+    for (i = 0; i < n_jobs; i++) {
+      if (jobs[i].threaded)
+        pthread_join(jobs[i].thread, NULL);
+      else
+        open_main(&jobs[i]);
+      if (jobs[i].dev)
+        ctx->dev[ctx->num_devices++] = jobs[i].dev;
+      else
+        snprintf(ctx->err, sizeof ctx->err, "%s", jobs[i].err);
+    }
+    free(jobs);
   }
   return ctx;
 }
@@ -104,9 +151,29 @@ int mcgpu_load_materials(mcgpu_ctx* ctx, const char* const* paths, int n_paths) 
   if ((rc = mcgpu_read_materials(ctx, paths, n_paths)) != MCGPU_OK) return rc;
   if ((rc = mcgpu_build_scene(ctx)) != MCGPU_OK) return rc;
   ctx->have_tables = 1;
-  if (ctx->have_input) {
-    for (i = 0; i < ctx->num_devices; i++)
-      if (mcgpu_dev_upload(ctx->dev[i], &ctx->scene, &ctx->vol, &ctx->spc, ctx->views[0].total_num_pixels, ctx->err, sizeof ctx->err) != 0) return MCGPU_E_CUDA;
+  if (ctx->have_input && ctx->num_devices > 0) { /* every device gets its own copy, uploaded concurrently (H:2612-2690 does one device per MPI rank) */
+    upload_job* jobs = (upload_job*)calloc((size_t)ctx->num_devices, sizeof *jobs);
+    if (!jobs) return mcgpu_fail(ctx, MCGPU_E_NOMEM, "load_material: out of memory");
+    rc = MCGPU_OK;
+    for (i = 0; i < ctx->num_devices; i++) {
+      jobs[i].ctx = ctx, jobs[i].device = i;
+      jobs[i].threaded = ctx->num_devices > 1 && pthread_create(&jobs[i].thread, NULL, upload_main, &jobs[i]) == 0;
+    }
+    for (i = 0; i < ctx->num_devices; i++) {
+      if (jobs[i].threaded)
+        pthread_join(jobs[i].thread, NULL);
+      else
+        upload_main(&jobs[i]);
+      if (jobs[i].rc != 0) {
+        snprintf(ctx->err, sizeof ctx->err, "%s", jobs[i].err);
+        rc = MCGPU_E_CUDA;
+      }
+    }
+    free(jobs);
+    if (rc != MCGPU_OK) {
+      ctx->have_tables = 0;
+      return rc;
+    }
   }
   return MCGPU_OK;
 }
