@@ -240,7 +240,100 @@ static int read_voxels_binary(mcgpu_ctx* ctx, gzFile f) {
   return mcgpu_finish_volume(ctx);
 }
 
+/* ---- content-addressed geometry cache ---------------------------------------------------------------
+ * cbctmc re-runs the same geometry file many times (air scan before every run-mc, force_rerun, speed-up and reference
+ * counts of one patient, simulation.py:116, 632-641), and a text geometry costs one sscanf-like pass per voxel (1.4 GB of
+ * text for 500^3).  With MCGPU_CACHE_DIR set, a text geometry is keyed by a 128-bit hash of its (compressed) file bytes
+ * and stored once as '<dir>/vox_<hash>.voxb' (the binary layout above); later loads of the same bytes read that file
+ * instead of tokenising text.  Off by default: the engine writes nothing the caller did not ask for. */
+static int file_hash128(const char* path, uint64_t out[2]) {
+  FILE* f = fopen(path, "rb");
+  unsigned char* buf;
+  uint64_t h0 = 0xcbf29ce484222325ull, h1 = 0x9e3779b97f4a7c15ull, total = 0;
+  size_t got;
+  if (!f) return -1;
+  buf = (unsigned char*)malloc(1 << 20);
+  if (!buf) {
+    fclose(f);
+    return -1;
+  }
+  while ((got = fread(buf, 1, 1 << 20, f)) > 0) {
+    size_t i = 0;
+    for (; i + 8 <= got; i += 8) { /* two independent multiply-xorshift lanes over 8-byte words */
+      uint64_t w;
+      memcpy(&w, buf + i, 8);
+      h0 = (h0 ^ w) * 0x100000001b3ull;
+      h0 ^= h0 >> 29;
+      h1 = (h1 + w) * 0xff51afd7ed558ccdull;
+      h1 ^= h1 >> 32;
+    }
+    for (; i < got; i++) {
+      h0 = (h0 ^ buf[i]) * 0x100000001b3ull;
+      h1 = (h1 + buf[i]) * 0xff51afd7ed558ccdull;
+      h1 ^= h1 >> 32;
+    }
+    total += got;
+  }
+  free(buf);
+  fclose(f);
+  out[0] = h0 ^ (total * 0x9e3779b97f4a7c15ull);
+  out[1] = h1 ^ (total << 1);
+  return 0;
+}
+
+static int write_voxels_binary(const mcgpu_volume* v, const char* path) {
+  char tmp[MCGPU_LINE + 96];
+  const uint32_t head[4] = {1u, (uint32_t)v->nx, (uint32_t)v->ny, (uint32_t)v->nz};
+  const size_t n = (size_t)v->nx * v->ny * v->nz;
+  FILE* f;
+  int ok;
+  snprintf(tmp, sizeof tmp, "%s.tmp%ld", path, (long)getpid());
+  f = fopen(tmp, "wb");
+  if (!f) return -1;
+  ok = fwrite("MCGPUVXB", 1, 8, f) == 8 && fwrite(head, sizeof head, 1, f) == 1 && fwrite(v->voxel_size, sizeof(float), 3, f) == 3 &&
+       fwrite(v->material, 1, n, f) == n && fwrite(v->density, sizeof(float), n, f) == n;
+  ok = (fclose(f) == 0) && ok;
+  if (!ok || rename(tmp, path) != 0) { /* atomic publish: concurrent runs of the same geometry never see half a file */
+    remove(tmp);
+    return -1;
+  }
+  return 0;
+}
+
+static int read_voxels_text(mcgpu_ctx* ctx, const char* path);
+
 int mcgpu_read_voxels(mcgpu_ctx* ctx, const char* path) {
+  const char* dir = getenv("MCGPU_CACHE_DIR");
+  char cached[MCGPU_LINE + 64];
+  uint64_t h[2];
+  int rc;
+  if (!dir || !*dir || strlen(dir) > MCGPU_LINE - 8) return read_voxels_text(ctx, path);
+  {
+    gzFile f = gzopen(path, "rb"); /* a binary geometry needs no cache */
+    char magic[8];
+    const int is_binary = f && gzread(f, magic, 8) == 8 && !memcmp(magic, "MCGPUVXB", 8);
+    if (f) gzclose(f);
+    if (!f || is_binary || file_hash128(path, h) != 0) return read_voxels_text(ctx, path);
+  }
+  snprintf(cached, sizeof cached, "%s/vox_%016llx%016llx.voxb", dir, (unsigned long long)h[0], (unsigned long long)h[1]);
+  {
+    gzFile f = gzopen(cached, "rb");
+    if (f) {
+      char magic[8];
+      rc = (gzread(f, magic, 8) == 8 && !memcmp(magic, "MCGPUVXB", 8)) ? read_voxels_binary(ctx, f) : MCGPU_E_PARSE;
+      gzclose(f);
+      if (rc == MCGPU_OK) {
+        if (ctx->verbose) printf("       geometry taken from the cache: %s\n", cached);
+        return rc;
+      }
+    }
+  }
+  if ((rc = read_voxels_text(ctx, path)) != MCGPU_OK) return rc;
+  if (write_voxels_binary(&ctx->vol, cached) != 0 && ctx->verbose) printf("       (geometry cache %s is not writable; continuing without it)\n", dir);
+  return MCGPU_OK;
+}
+
+static int read_voxels_text(mcgpu_ctx* ctx, const char* path) {
   char line[MCGPU_LINE];
   int nx = 0, ny = 0, nz = 0, rc = MCGPU_OK, n_threads, i, eof = 0;
   float size[3] = {0.f, 0.f, 0.f};

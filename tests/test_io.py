@@ -1,8 +1,9 @@
 """Voxel-file ingest (text, gzip, in-memory), palette packing, and their error behaviour
 (reference: load_voxels, MC-GPU_v1.3.cu:1996-2145)."""
 import gzip
+from pathlib import Path
 
-import numpy as np
+import numpy as np  # noqa
 import pytest
 
 
@@ -267,3 +268,44 @@ def test_every_material_of_the_patient_set_ships_in_full(pkg):
     for _, ident, _, path in rows:
         text = gzip.open(path, "rt").read()
         assert "STUB" not in text and text.count("\n") > 20000, ident
+
+
+def test_content_addressed_geometry_cache(pkg, cases, tmp_path, monkeypatch):
+    """MCGPU_CACHE_DIR (SURVEY 8f-2): a text geometry is stored once as a binary file named after the hash of its bytes;
+    the same bytes load from it (same volume, same packing), other bytes get another entry, a corrupt entry is ignored,
+    and without the variable nothing is written."""
+    inp, cfg, ph = cases["thorax_p4"]
+    vox = Path(inp).parent / "geometry.vox.gz"
+    cache = tmp_path / "cache"
+    cache.mkdir()
+
+    def volume():
+        with load(pkg, inp) as eng:
+            eng.load_voxels(vox)
+            return eng.table("voxel_material").copy(), eng.table("voxel_density").copy(), eng.table("voxel_packed").copy(), eng.info.voxel_bits
+
+    plain = volume()
+    assert list(cache.iterdir()) == []
+    monkeypatch.setenv("MCGPU_CACHE_DIR", str(cache))
+    first = volume()
+    entries = list(cache.iterdir())
+    assert len(entries) == 1 and entries[0].name.startswith("vox_") and entries[0].suffix == ".voxb"
+    mtime = entries[0].stat().st_mtime_ns
+    second = volume()  # served from the cache: the entry is not rewritten
+    assert list(cache.iterdir()) == entries and entries[0].stat().st_mtime_ns == mtime
+    for a, b, c in zip(plain, first, second):
+        assert np.array_equal(a, b) and np.array_equal(a, c)
+    # the cache file is the documented binary geometry: loading it directly gives the same volume
+    with load(pkg, inp) as eng:
+        eng.load_voxels(entries[0])
+        assert np.array_equal(eng.table("voxel_packed"), plain[2])
+    # other bytes -> another entry
+    other = tmp_path / "other.vox.gz"
+    pkg.mcio.write_vox(other, ph.materials[::-1].copy(), ph.densities[::-1].copy(), ph.spacing_cm)
+    with load(pkg, inp) as eng:
+        eng.load_voxels(other)
+    assert len(list(cache.iterdir())) == 2
+    # a damaged entry is not trusted: the text is parsed again and the entry replaced
+    entries[0].write_bytes(b"MCGPUVXB" + b"\0" * 10)
+    third = volume()
+    assert np.array_equal(third[2], plain[2]) and entries[0].stat().st_size > 1000
