@@ -292,8 +292,18 @@ extern "C" struct mcgpu_reducer* mcgpu_dev_reducer_create(struct mcgpu_device** 
   if (!r) return NULL;
   r->n = n;
   for (int k = 0; k < n; k++) r->dev[k] = devs[k];
-  const char* want = getenv("MCGPU_REDUCE");  // "nccl" (default) | "peer"
-  const NcclApi* api = (want && !strcmp(want, "peer")) ? NULL : nccl_api();
+  // MCGPU_REDUCE = "peer" | "nccl".  Default: the peer kernel when every device can map device 0's peers (NVLink/NVSwitch boxes),
+  // NCCL otherwise.  Both move the same bytes at the same speed (0.42 ms for 7 x 45 MB on 8 x B200), but ncclCommInitAll costs
+  // ~2.5 s per process on 8 GPUs, which the air scan -- ONE projection per process, run before every run-mc -- would pay in full.
+  const char* want = getenv("MCGPU_REDUCE");
+  bool all_peers = true;
+  for (int k = 1; k < n; k++) {
+    int can = 0;
+    if (cudaDeviceCanAccessPeer(&can, devs[0]->ordinal, devs[k]->ordinal) != cudaSuccess || !can) all_peers = false;
+  }
+  cudaGetLastError();
+  const bool try_nccl = want ? !strcmp(want, "nccl") : !all_peers;
+  const NcclApi* api = try_nccl ? nccl_api() : NULL;
   if (api) {
     int ids[MCGPU_MAX_PEERS];
     for (int k = 0; k < n; k++) ids[k] = devs[k]->ordinal;

@@ -61,7 +61,7 @@ mcgpu_ctx* mcgpu_create(const int* device_ids, int n_devices) {
     free(ctx);
     return NULL;
   }
-  { /* CUDA context creation costs ~0.5 s per device: open the devices concurrently (one short-lived thread each) */
+  { /* CUDA context creation costs ~0.3-1 s per device (more on a cold driver): open the devices concurrently, in the background */
     open_job* jobs = (open_job*)calloc((size_t)n_devices, sizeof *jobs);
     int n_jobs = 0;
     if (!jobs) {
@@ -76,25 +76,40 @@ mcgpu_ctx* mcgpu_create(const int* device_ids, int n_devices) {
       if (dup) continue;
       jobs[n_jobs++].ordinal = id;
     }
-    for (i = 0; i < n_jobs; i++) jobs[i].threaded = n_jobs > 1 && pthread_create(&jobs[i].thread, NULL, open_main, &jobs[i]) == 0;
-    for (i = 0; i < n_jobs; i++) {
-      if (jobs[i].threaded)
-        pthread_join(jobs[i].thread, NULL);
-      else
-        open_main(&jobs[i]);
-      if (jobs[i].dev)
-        ctx->dev[ctx->num_devices++] = jobs[i].dev;
-      else
-        snprintf(ctx->err, sizeof ctx->err, "%s", jobs[i].err);
-    }
-    free(jobs);
+    /* the threads run on while the caller parses the input files; whoever needs a device first joins them (mcgpu_devices_ready) */
+    for (i = 0; i < n_jobs; i++) jobs[i].threaded = pthread_create(&jobs[i].thread, NULL, open_main, &jobs[i]) == 0;
+    ctx->opening = jobs;
+    ctx->n_opening = n_jobs;
   }
   return ctx;
+}
+
+/* Join the background device opens of mcgpu_create (idempotent); devices that could not be opened are dropped. */
+void mcgpu_devices_ready(mcgpu_ctx* ctx) {
+  open_job* jobs;
+  int i;
+  if (!ctx || !ctx->opening) return;
+  jobs = (open_job*)ctx->opening;
+  for (i = 0; i < ctx->n_opening; i++) {
+    if (jobs[i].threaded)
+      pthread_join(jobs[i].thread, NULL);
+    else
+      open_main(&jobs[i]);
+    if (jobs[i].dev) {
+      mcgpu_dev_set_fast_math(jobs[i].dev, ctx->fast_math);
+      ctx->dev[ctx->num_devices++] = jobs[i].dev;
+    } else
+      snprintf(ctx->err, sizeof ctx->err, "%s", jobs[i].err);
+  }
+  free(jobs);
+  ctx->opening = NULL;
+  ctx->n_opening = 0;
 }
 
 void mcgpu_destroy(mcgpu_ctx* ctx) {
   int i;
   if (!ctx) return;
+  mcgpu_devices_ready(ctx);
   mcgpu_dev_reducer_free(ctx->reducer);
   for (i = 0; i < ctx->num_devices; i++) mcgpu_dev_close(ctx->dev[i]);
   free(ctx->dev);
@@ -151,6 +166,7 @@ int mcgpu_load_materials(mcgpu_ctx* ctx, const char* const* paths, int n_paths) 
   if ((rc = mcgpu_read_materials(ctx, paths, n_paths)) != MCGPU_OK) return rc;
   if ((rc = mcgpu_build_scene(ctx)) != MCGPU_OK) return rc;
   ctx->have_tables = 1;
+  mcgpu_devices_ready(ctx);
   if (ctx->have_input && ctx->num_devices > 0) { /* every device gets its own copy, uploaded concurrently (H:2612-2690 does one device per MPI rank) */
     upload_job* jobs = (upload_job*)calloc((size_t)ctx->num_devices, sizeof *jobs);
     if (!jobs) return mcgpu_fail(ctx, MCGPU_E_NOMEM, "load_material: out of memory");
@@ -190,6 +206,7 @@ int mcgpu_set_fast_math(mcgpu_ctx* ctx, int on) {
   int d;
   if (!ctx) return MCGPU_E_ARG;
   ctx->fast_math = on != 0;
+  mcgpu_devices_ready(ctx);
   for (d = 0; d < ctx->num_devices; d++) mcgpu_dev_set_fast_math(ctx->dev[d], ctx->fast_math);
   return MCGPU_OK;
 }
@@ -237,6 +254,7 @@ int mcgpu_projection_seed(mcgpu_ctx* ctx, int p, int* seed_out) {
 
 static int ready_to_run(mcgpu_ctx* ctx, int p) {
   if (!ctx) return MCGPU_E_ARG;
+  mcgpu_devices_ready(ctx);
   if (!ctx->have_input || !ctx->have_voxels || !ctx->have_tables) return mcgpu_fail(ctx, MCGPU_E_STATE, "run: input, voxels and materials must be loaded first");
   if (ctx->num_devices < 1) return mcgpu_fail(ctx, MCGPU_E_CUDA, "run: no usable CUDA device (there is no CPU fallback)");
   if (p < 0 || p >= ctx->in.num_projections) return mcgpu_fail(ctx, MCGPU_E_ARG, "run: projection %d out of range [0,%d)", p, ctx->in.num_projections);
@@ -313,12 +331,16 @@ int mcgpu_run_projection(mcgpu_ctx* ctx, int p, uint64_t* image_host) {
   return MCGPU_OK;
 }
 
-void* mcgpu_device_image(mcgpu_ctx* ctx) { return (ctx && ctx->num_devices > 0) ? mcgpu_dev_image_ptr(ctx->dev[0]) : NULL; }
+void* mcgpu_device_image(mcgpu_ctx* ctx) {
+  mcgpu_devices_ready(ctx);
+  return (ctx && ctx->num_devices > 0) ? mcgpu_dev_image_ptr(ctx->dev[0]) : NULL;
+}
 double mcgpu_last_kernel_ms(const mcgpu_ctx* ctx) { return ctx ? ctx->last_kernel_ms : 0.0; }
 double mcgpu_last_reduce_ms(const mcgpu_ctx* ctx) { return ctx ? ctx->last_reduce_ms : 0.0; }
 const char* mcgpu_reduce_kind(const mcgpu_ctx* ctx) { return ctx ? mcgpu_dev_reducer_kind(ctx->reducer) : "none"; }
 int mcgpu_device_selftest(mcgpu_ctx* ctx, const char* name, unsigned long long* mismatches) {
   if (!ctx || !name || !mismatches) return MCGPU_E_ARG;
+  mcgpu_devices_ready(ctx);
   if (ctx->num_devices < 1) return mcgpu_fail(ctx, MCGPU_E_CUDA, "selftest: no usable CUDA device");
   return mcgpu_dev_selftest(ctx->dev[0], name, mismatches, ctx->err, sizeof ctx->err) == 0 ? MCGPU_OK : MCGPU_E_CUDA;
 }
@@ -566,6 +588,7 @@ int mcgpu_get_info(const mcgpu_ctx* ctx, mcgpu_info* out) {
   int hpt, blocks = 0;
   unsigned long long launched = 0;
   if (!ctx || !out) return MCGPU_E_ARG;
+  mcgpu_devices_ready((mcgpu_ctx*)ctx); /* num_devices counts the devices that really opened */
   memset(out, 0, sizeof *out);
   out->num_devices = ctx->num_devices;
   out->fast_math = ctx->fast_math;
@@ -650,6 +673,7 @@ long long mcgpu_copy_table(const mcgpu_ctx* ctx, const char* name, void* out, si
 int mcgpu_reset_dose(mcgpu_ctx* ctx) {
   int d;
   if (!ctx || !ctx->have_tables) return MCGPU_E_STATE;
+  mcgpu_devices_ready(ctx);
   for (d = 0; d < ctx->num_devices; d++)
     if (mcgpu_dev_reset_dose(ctx->dev[d], ctx->err, sizeof ctx->err) != 0) return MCGPU_E_CUDA;
   return MCGPU_OK;
@@ -665,6 +689,7 @@ long long mcgpu_get_dose(mcgpu_ctx* ctx, const char* which, uint64_t* out, size_
   if (!out) return (long long)words;
   if (cap_words < words) return mcgpu_fail(ctx, MCGPU_E_ARG, "get_dose: buffer of %zu words, %zu needed", cap_words, words);
   memset(out, 0, words * sizeof(uint64_t));
+  mcgpu_devices_ready(ctx);
   for (d = 0; d < ctx->num_devices; d++)
     if (mcgpu_dev_add_dose(ctx->dev[d], materials ? out : NULL, materials ? NULL : out, ctx->err, sizeof ctx->err) != 0) return MCGPU_E_CUDA;
   return (long long)words;

@@ -50,12 +50,26 @@ static int die(mcgpu_ctx* ctx, int rc) {
   return rc;
 }
 
+static double seconds_since(const struct timespec* t0) {
+  struct timespec t;
+  clock_gettime(CLOCK_MONOTONIC, &t);
+  return (t.tv_sec - t0->tv_sec) + 1e-9 * (t.tv_nsec - t0->tv_nsec);
+}
+
 static int load_one(mcgpu_ctx* ctx, const char* in_path, int quiet) {
+  struct timespec t0;
+  double t_in, t_vox;
   int rc;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
   if (!quiet) printf("\n    -- Reading the input file '%s':\n", in_path);
   if ((rc = mcgpu_load_input(ctx, in_path)) != MCGPU_OK) return rc;
+  t_in = seconds_since(&t0);
   if ((rc = mcgpu_load_voxels(ctx, NULL)) != MCGPU_OK) return rc;
-  return mcgpu_load_materials(ctx, NULL, 0);
+  t_vox = seconds_since(&t0);
+  rc = mcgpu_load_materials(ctx, NULL, 0);
+  if (!quiet && rc == MCGPU_OK) /* the devices are opened in the background meanwhile; the last stage waits for them and uploads */
+    printf("       input + spectrum + poses %.3f s, voxels %.3f s, material tables + waiting for the devices + upload %.3f s\n", t_in, t_vox - t_in, seconds_since(&t0) - t_vox);
+  return rc;
 }
 
 static int simulate_one(mcgpu_ctx* ctx, const struct timespec* t0) {
@@ -152,6 +166,7 @@ int main(int argc, char** argv) {
   fflush(stdout);
 
   ctx = mcgpu_create(NULL, 0); /* every visible device; a .in gpu id that is out of range means the same (Q13) */
+  printf("       CUDA driver initialised in %.3f s; the devices are being opened in the background\n", seconds_since(&t0));
   if (!ctx) {
     printf("\n\n   !!out of memory creating the context!!\n\n");
     return -4;

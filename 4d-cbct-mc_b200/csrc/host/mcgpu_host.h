@@ -146,6 +146,8 @@ struct mcgpu_ctx {
                                       which the NEXT projection's grid rule starts from; 0 = the .in value */
   int num_devices;
   struct mcgpu_device** dev;
+  void* opening;     /* device opens still running in the background (mcgpu_create); joined by mcgpu_devices_ready */
+  int n_opening;
   double last_kernel_ms;
   double last_reduce_ms;            /* history-split runs: device time of the reduction of the partial images */
   struct mcgpu_reducer* reducer;    /* created on the first multi-device projection, for reducer_devices devices */
@@ -166,6 +168,7 @@ void mcgpu_free_volume(mcgpu_volume* v);
 void mcgpu_free_tables(mcgpu_tables* t);
 void mcgpu_free_scene(mcgpu_scene* s);
 int mcgpu_fail(mcgpu_ctx* ctx, int code, const char* fmt, ...);
+void mcgpu_devices_ready(mcgpu_ctx* ctx); /* api.c: join the background device opens; call before touching ctx->dev / num_devices */
 /* grid of the projection(s) simulated last (or of the first one before any run): sticky hpt AND sticky history count */
 void mcgpu_current_grid(const mcgpu_ctx* ctx, int* hpt, int* blocks, unsigned long long* launched);
 char* mcgpu_fgets_trimmed(char* out, int num, FILE* f);

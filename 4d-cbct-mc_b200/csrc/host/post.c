@@ -18,6 +18,7 @@ int mcgpu_post_intensity(mcgpu_ctx* ctx, const uint64_t* tally, unsigned long lo
   double norm;
   const double scale = 1.0 / 100.0f; /* SCALE_eV, as in report_image (H:2860-2861) */
   if (!ctx || !ctx->have_input) return MCGPU_E_ARG;
+  mcgpu_devices_ready(ctx);
   if (ctx->num_devices < 1) return mcgpu_fail(ctx, MCGPU_E_CUDA, "post_intensity: no CUDA device (this engine has no CPU path)");
   v0 = &ctx->views[0];
   if (crop_x <= 0 || crop_x > v0->num_pixels_x) crop_x = v0->num_pixels_x;
@@ -88,6 +89,7 @@ int mcgpu_post_gaussian(mcgpu_ctx* ctx, const float* in, int n0, int n1, double 
   double *w0 = NULL, *w1 = NULL;
   int r0 = 0, r1 = 0, rc;
   if (!ctx || !in || !out || n0 < 1 || n1 < 1) return MCGPU_E_ARG;
+  mcgpu_devices_ready(ctx);
   if (ctx->num_devices < 1) return mcgpu_fail(ctx, MCGPU_E_CUDA, "post_gaussian: no CUDA device (this engine has no CPU path)");
   if (sigma0 > 1e-15 && (r0 = gaussian_weights(sigma0, &w0)) < 0) return mcgpu_fail(ctx, MCGPU_E_NOMEM, "post_gaussian: out of memory");
   if (sigma1 > 1e-15 && (r1 = gaussian_weights(sigma1, &w1)) < 0) {
@@ -101,6 +103,7 @@ int mcgpu_post_gaussian(mcgpu_ctx* ctx, const float* in, int n0, int n1, double 
 
 int mcgpu_post_normalize(mcgpu_ctx* ctx, const float* air, float* stack, long long n_images, int n0, int n1, float min_nonzero) {
   if (!ctx || !air || !stack || n_images < 0 || n0 < 1 || n1 < 1) return MCGPU_E_ARG;
+  mcgpu_devices_ready(ctx);
   if (ctx->num_devices < 1) return mcgpu_fail(ctx, MCGPU_E_CUDA, "post_normalize: no CUDA device (this engine has no CPU path)");
   if (n_images == 0) return MCGPU_OK;
   return mcgpu_dev_post_normalize(ctx->dev[0], air, stack, n_images, n0, n1, min_nonzero, ctx->err, sizeof ctx->err) == 0 ? MCGPU_OK : MCGPU_E_CUDA;

@@ -120,9 +120,10 @@ void* mcgpu_device_image(mcgpu_ctx* ctx);
 double mcgpu_last_kernel_ms(const mcgpu_ctx* ctx);
 
 /* History-split runs (several devices, one projection): device time of the reduction of the partial images in the last
- * mcgpu_run_projection, and how it was done: "ncclReduce" (libnccl over NVLink/NVSwitch; the reference: MPI_Reduce, H:1019),
- * "peer-kernel" (one kernel reading every peer's image through NVLink peer mappings; when libnccl cannot be loaded or the
- * environment has MCGPU_REDUCE=peer), "staged-copy" (no peer access) or "none". */
+ * mcgpu_run_projection (the reference: MPI_Reduce, H:1019), and how it was done: "peer-kernel" (ONE kernel on device 0 reading
+ * every peer's image through NVLink peer mappings; the default where all devices are peers), "ncclReduce" (ncclUint64 sum over
+ * NVLink/NVSwitch, one communicator per device, libnccl opened at run time; default without full peer access, or with
+ * MCGPU_REDUCE=nccl in the environment), "staged-copy" (neither) or "none". */
 double mcgpu_last_reduce_ms(const mcgpu_ctx* ctx);
 const char* mcgpu_reduce_kind(const mcgpu_ctx* ctx);
 
