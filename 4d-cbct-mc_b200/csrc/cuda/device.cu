@@ -129,8 +129,8 @@ extern "C" int mcgpu_dev_upload(struct mcgpu_device* d, const mcgpu_scene* s, co
   d->image_words = (size_t)4 * npix_total;
   if (upload(&d->d_image, NULL, sizeof(unsigned long long) * d->image_words, err, errlen)) return -1;
   CK(cudaMemset(d->d_image, 0, sizeof(unsigned long long) * d->image_words));
-  CK(cudaMalloc((void**)&d->d_stream_counter, 2 * sizeof(unsigned long long)));
-  CK(cudaMemset(d->d_stream_counter, 0, 2 * sizeof(unsigned long long)));
+  CK(cudaMalloc((void**)&d->d_stream_counter, 16 * sizeof(unsigned long long)));  // [2..12]: MCGPU_WF_STATS diagnostics
+  CK(cudaMemset(d->d_stream_counter, 0, 16 * sizeof(unsigned long long)));
   d->dose_roi_voxels = 0;
   if (s->tally_material_dose) {
     CK(cudaMalloc((void**)&d->d_materials_dose, sizeof(unsigned long long) * 2 * MCGPU_MAX_MATERIALS));
@@ -200,6 +200,16 @@ extern "C" int mcgpu_dev_sync(struct mcgpu_device* d, float* kernel_ms, char* er
     *kernel_ms = 0.f;
     if (d->timed) CK(cudaEventElapsedTime(kernel_ms, d->ev0, d->ev1));
   }
+#ifdef MCGPU_WF_STATS
+  if (d->d_stream_counter) {
+    unsigned long long s[11];
+    CK(cudaMemcpy(s, d->d_stream_counter + 2, sizeof s, cudaMemcpyDeviceToHost));
+    CK(cudaMemset(d->d_stream_counter + 2, 0, sizeof s));
+    const char* qn[4] = {"W", "N", "C", "R"};
+    for (int q = 0; q < 4; q++) fprintf(stderr, "wf_stats %s: %llu batches, %.2f contexts per batch\n", qn[q], s[q], s[q] ? (double)s[4 + q] / s[q] : 0.0);
+    fprintf(stderr, "wf_stats tracking: %.2f steps per batch, %.2f lanes per step; idle polls %llu\n", s[0] ? (double)s[8] / s[0] : 0.0, s[8] ? (double)s[9] / s[8] : 0.0, s[10]);
+  }
+#endif
   if (d->kernel_generation == 3 && d->d_stream_counter) {  // the wavefront kernel reports a lost context instead of hanging
     unsigned long long flag = 0;
     CK(cudaMemcpy(&flag, d->d_stream_counter + 1, sizeof flag, cudaMemcpyDeviceToHost));

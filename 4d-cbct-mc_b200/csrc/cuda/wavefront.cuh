@@ -132,6 +132,12 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
 #define PF(f) pool[pid * MCGPU_WF_STRIDE + (f)]
 #define PI(f) pool_i[pid * MCGPU_WF_STRIDE + (f)]
 
+#ifdef MCGPU_WF_STATS  // diagnostics build (make ... XFLAGS=-DMCGPU_WF_STATS): batch sizes per queue, tracking steps, idle polls
+  unsigned long long st_pops[Q_COUNT] = {0, 0, 0, 0}, st_lanes[Q_COUNT] = {0, 0, 0, 0}, st_wsteps = 0, st_wlanes = 0, st_idle = 0;
+#define WF_STAT(x) x
+#else
+#define WF_STAT(x)
+#endif
   for (;;) {
     // ------------------------------------------------------------------ acquire a batch: up to 32 ids of one queue
     int q = 0, n = 0;
@@ -164,6 +170,7 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
               break;
             }
           }
+          WF_STAT(st_idle++;)
           __nanosleep(200);
           continue;
         }
@@ -180,6 +187,7 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
       q = (int)(packed & 3u), n = (int)((packed >> 2) & 63u), pos = packed >> 8;
     }
     if (n <= 0) break;
+    WF_STAT(st_pops[q]++; st_lanes[q] += n;)
 
     bool act = (int)lane < n;
     int pid = 0;
@@ -262,6 +270,7 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
             }
           }
         }
+        WF_STAT(st_wsteps++; st_wlanes += __popc(__ballot_sync(MCGPU_FULL_MASK, state == ST_W));)
       } while (__popc(__ballot_sync(MCGPU_FULL_MASK, state == ST_W)) >= thr);
     } else if (q == Q_N) {
       // ---------------------------------------------------------------- T / I / N: tally, next stream, next history
@@ -407,6 +416,14 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
       if (m_f && lane == 0) atomicSub(&ctl->live, __popc(m_f));
     }
   }
+#ifdef MCGPU_WF_STATS
+  if (lane == 0) {
+    unsigned long long* g = stream_counter + 2;
+    for (int t = 0; t < Q_COUNT; t++) atomicAdd(g + t, st_pops[t]), atomicAdd(g + 4 + t, st_lanes[t]);
+    atomicAdd(g + 8, st_wsteps), atomicAdd(g + 9, st_wlanes), atomicAdd(g + 10, st_idle);
+  }
+#endif
+#undef WF_STAT
 #undef PF
 #undef PI
 }

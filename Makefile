@@ -38,7 +38,7 @@ $(BUILD)/%.o: $(HOSTDIR)/%.c $(HOSTDIR)/mcgpu_host.h include/mcgpu_b200.h
 
 $(BUILD)/device.o: $(CUDADIR)/device.cu $(CUDA_HDR)
 	@mkdir -p $(BUILD)
-	$(NVCC) $(NVFLAGS) -fmad=false -c $< -o $@
+	$(NVCC) $(NVFLAGS) -fmad=false $(XFLAGS) -c $< -o $@
 
 $(BUILD)/postprocess.o: $(CUDADIR)/postprocess.cu $(CUDA_HDR)
 	@mkdir -p $(BUILD)
@@ -69,6 +69,11 @@ $(BINDIR)/MC-GPU_v1.3_batch.x: $(HOSTDIR)/main.c $(LIBDIR)/libmcgpu_b200.so
 	$(CC) $(CFLAGS) -DMCGPU_BATCH_MAIN -fPIE $< -o $@ -L$(LIBDIR) -lmcgpu_b200 -lpthread -Wl,-rpath,'$$ORIGIN/../lib'
 
 # microbenchmarks that pin the hardware denominators of the rooflines (instruction cache, u64 atomics, L2 random gather)
+# diagnostics build of the library: batch sizes per queue, tracking steps per batch, idle polls printed to stderr after every launch
+#   make stats  ->  4d-cbct-mc_b200/lib_stats/libmcgpu_b200.so   (use with MCGPU_B200_LIB=...)
+stats:
+	$(MAKE) BUILD=build_stats LIBDIR=$(PKG)/lib_stats XFLAGS=-DMCGPU_WF_STATS lib
+
 ubench: tools/ubench/bin/icache tools/ubench/bin/atomics tools/ubench/bin/l2gather
 tools/ubench/bin/%: tools/ubench/%.cu
 	@mkdir -p tools/ubench/bin
@@ -78,4 +83,4 @@ clean:
 	rm -rf $(BUILD) $(LIBDIR) $(BINDIR) tools/ubench/bin
 	$(MAKE) -C oracle clean
 
-.PHONY: all lib exe oracle ubench clean
+.PHONY: all lib exe oracle ubench stats clean

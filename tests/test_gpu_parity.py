@@ -248,10 +248,14 @@ def test_full_size_properties(pkg, gpu_engine_factory, tmp_path):
     eng.close()
 
 
-def test_history_split_across_two_gpus_is_bit_identical(pkg, cases):
+@pytest.mark.parametrize("reduce", ["peer", "nccl"])
+def test_history_split_across_two_gpus_is_bit_identical(pkg, cases, reduce, monkeypatch):
+    """mcgpu_run_projection on a multi-device context: block ranges of the reference grid per device, u64 tallies summed on
+    device 0 by the one-kernel peer reduce or by ncclReduce (the reference: MPI_Reduce, H:1019)."""
     out = subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True).stdout
     if out.count("GPU ") < 2:
         pytest.skip("needs 2 GPUs")
+    monkeypatch.setenv("MCGPU_REDUCE", reduce)
     inp, cfg, _ = cases["thorax_p4"]
     one = pkg.engine.Engine([0])
     one.load_input(inp).load_voxels().load_materials()
@@ -259,6 +263,8 @@ def test_history_split_across_two_gpus_is_bit_identical(pkg, cases):
     two.load_input(inp).load_voxels().load_materials()
     assert two.info.num_devices == 2
     assert np.array_equal(one.run_projection(3), two.run_projection(3))
+    assert two.reduce_kind == ("peer-kernel" if reduce == "peer" else "ncclReduce") and two.last_reduce_ms > 0
+    assert one.reduce_kind == "none"
     one.close()
     two.close()
 
