@@ -17,11 +17,14 @@
 // time and its stream is advanced strictly in order, so every float of every trajectory and hence
 // every integer tally is identical to generations 1 and 2 and to the reference (tested).
 //
-// Queues are rings of 16-bit ids in shared memory: `tail` is reserved with one warp-aggregated
-// atomicAdd per push, entries are published individually (an entry is EMPTY until written),
-// `avail` counts published entries and is claimed with atomicCAS by the popping warp, `head` gives
-// it its ring positions.  No locks; the only waits are on an entry that is reserved but not yet
-// written, and they are bounded (a watchdog raises the launch's error flag instead of hanging).
+// Queues are rings of 16-bit ids in shared memory with two counters each: producers reserve `tail` with one
+// warp-aggregated atomicAdd per push and then write their entries (an entry is EMPTY until written); a popping
+// warp claims [head, head + n) with ONE atomicCAS on `head`, n <= tail - head, and reads its entries, waiting for
+// the few that are reserved but not written yet.  Two shared-memory atomics per batch exchange in total: the
+// exchange is a chain of dependent long-latency operations on the warp's critical path, and what it costs is that
+// latency (~600 issue slots per exchange beyond its ~230 instructions, measured through the tracking threshold:
+// DESIGN.md 10), not its instruction count.  No locks; all waits are bounded (a watchdog raises the launch's
+// error flag instead of hanging).
 //
 // Code size is a first-class constraint here: with exact arithmetic the kernel was bound by instruction-
 // cache misses until its hot code fitted the SM's 32 KB instruction cache.  Hence ONE
@@ -35,17 +38,18 @@ namespace MCGPU_NS {
 
 #define MCGPU_WF_MAX_BLOCK 1024
 #define MCGPU_WF_EMPTY 0xffffu
-#define MCGPU_WF_FIELDS 12
+#define MCGPU_WF_FIELDS 13
 #define MCGPU_WF_STRIDE 13  // words per context in the pool: odd, so contexts spread over the shared-memory banks
 #define MCGPU_WF_MAX_POOL 2048
 
 enum WfQueue : int { Q_W = 0, Q_N = 1, Q_C = 2, Q_R = 3, Q_COUNT = 4 };
-enum WfField : int { F_X = 0, F_Y, F_Z, F_U, F_V, F_W, F_E, F_S1, F_S2, F_S0, F_HIST, F_META };
+// F_MFPW: the Woodcock mean free path at the photon's energy (K:246-247), fetched when the photon enters the tracking state so
+// that a tracking batch starts without a dependent L2 access
+enum WfField : int { F_X = 0, F_Y, F_Z, F_U, F_V, F_W, F_E, F_S1, F_S2, F_S0, F_HIST, F_META, F_MFPW };
 
 struct WfControl {
-  unsigned head[Q_COUNT];
-  unsigned tail[Q_COUNT];
-  int avail[Q_COUNT];
+  unsigned head[Q_COUNT];  // next ring position to pop (claimed by CAS)
+  unsigned tail[Q_COUNT];  // next ring position to push (reserved by atomicAdd); tail - head = entries waiting (written or about to be)
   int live;          // contexts that still have work (not finished)
   int active_warps;  // warps that have not retired
   int phase;         // queue the CTA is draining (sticky scheduling)
@@ -112,9 +116,8 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
     pool_i[i * MCGPU_WF_STRIDE + F_S2] = 1;
   }
   if (threadIdx.x == 0) {
-    for (int t = 0; t < Q_COUNT; t++) ctl->head[t] = 0u, ctl->tail[t] = 0u, ctl->avail[t] = 0;
+    for (int t = 0; t < Q_COUNT; t++) ctl->head[t] = 0u, ctl->tail[t] = 0u;
     ctl->tail[Q_N] = (unsigned)pool_size;
-    ctl->avail[Q_N] = pool_size;
     ctl->live = pool_size;
     ctl->active_warps = (int)(blockDim.x >> 5);
     ctl->phase = Q_N;
@@ -125,7 +128,8 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
   const unsigned lt_mask = (1u << lane) - 1u;
   float* wbuf = sh_scratch + (threadIdx.x >> 5) * rows * stride;
   const long long n_streams = stream_end - stream_begin;
-  volatile int* v_avail = ctl->avail;
+  volatile unsigned* v_head = ctl->head;
+  volatile unsigned* v_tail = ctl->tail;
   volatile int* v_live = &ctl->live;
   volatile int* v_phase = &ctl->phase;
 
@@ -145,7 +149,9 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
     if (lane == 0) {
       int idle = 0;
       for (;;) {
-        const int a0 = v_avail[0], a1 = v_avail[1], a2 = v_avail[2], a3 = v_avail[3];
+        // heads first, then tails: a tail read later can only be larger, so tail - head never overstates what the CAS below claims
+        const unsigned h0 = v_head[0], h1 = v_head[1], h2 = v_head[2], h3 = v_head[3];
+        const int a0 = (int)(v_tail[0] - h0), a1 = (int)(v_tail[1] - h1), a2 = (int)(v_tail[2] - h2), a3 = (int)(v_tail[3] - h3);
         int best = -1, a = 0;
         {  // keep draining the queue the CTA is working on, then move to the fullest one: most warps of
            // the CTA run the same kind of code, which is what the SM's 32 KB instruction cache rewards
@@ -175,9 +181,9 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
           continue;
         }
         const int take = a < 32 ? a : 32;
-        if (atomicCAS(&ctl->avail[best], a, a - take) == a) {
-          q = best, n = take;
-          pos = atomicAdd(&ctl->head[best], (unsigned)take);
+        const unsigned h = best == Q_W ? h0 : best == Q_N ? h1 : best == Q_C ? h2 : h3;
+        if (atomicCAS(&ctl->head[best], h, h + (unsigned)take) == h) {
+          q = best, n = take, pos = h;
           break;
         }
       }
@@ -213,7 +219,7 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
     Photon p;
     Ranecu rng;
     int state = ST_F, slot = 0, scatter_state = 0, hist_left = 0;
-    float s0 = 0.f;
+    float s0 = 0.f, mfpw = 0.f;
     p.x = p.y = p.z = p.u = p.v = p.w = p.E = 0.f;
     rng.s1 = rng.s2 = 1;
     if (act) {  // one load / store site for every kind of batch keeps the code small (the kernel is instruction-cache bound)
@@ -223,6 +229,7 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
       p.x = PF(F_X), p.y = PF(F_Y), p.z = PF(F_Z), p.u = PF(F_U), p.v = PF(F_V), p.w = PF(F_W), p.E = PF(F_E);
       s0 = PF(F_S0);
       hist_left = PI(F_HIST);
+      mfpw = PF(F_MFPW);
     }
 
     if (q == Q_W) {
@@ -233,8 +240,7 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
       int index = 0, slot_old = -1;
       if (act) {
         index = __float2int_rd((p.E - sc.e0) * sc.ide);
-        const float2 w = __ldg(&sc.woodcock[index]);
-        mfp_woodcock = w.x + p.E * w.y;
+        mfp_woodcock = mfpw;
       }
       const int thr = min(w_threshold, (n + 1) >> 1);
       do {
@@ -305,6 +311,10 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
           const bool enters = emit_photon<ROT>(sc, vw, st, rng, p);
           scatter_state = 0;
           state = enters ? ST_W : ST_T;  // a primary that misses the voxels can still hit the detector (K:240-241)
+          if (enters) {  // K:246-247, for the tracking batches to come
+            const float2 wc = __ldg(&sc.woodcock[__float2int_rd((p.E - sc.e0) * sc.ide)]);
+            mfpw = wc.x + p.E * wc.y;
+          }
         }
         if (__popc(__ballot_sync(MCGPU_FULL_MASK, state == ST_T)) < thr) break;
       }
@@ -369,6 +379,8 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
           if (index > -1) {
             scatter_state = (scatter_state == 0) ? 1 : 3;
             state = ST_W;
+            const float2 wc = __ldg(&sc.woodcock[index]);  // the energy changed: K:308-309
+            mfpw = wc.x + p.E * wc.y;
           } else {
             state = ST_N;  // below the tabulated energies: absorbed (K:311, K:372)
           }
@@ -385,6 +397,7 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
         PF(F_U) = p.u, PF(F_V) = p.v, PF(F_W) = p.w, PF(F_E) = p.E;
         PF(F_S0) = s0;
         PI(F_HIST) = hist_left;
+        PF(F_MFPW) = mfpw;
       }
     }
     __threadfence_block();
@@ -407,9 +420,6 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
         }
         *e = (unsigned short)pid;
       }
-      __threadfence_block();
-      __syncwarp();
-      if (nq >= 0 && (int)lane == leader) atomicAdd(&ctl->avail[nq], cnt);
     }
     {
       const unsigned m_f = __ballot_sync(MCGPU_FULL_MASK, act && state == ST_F);

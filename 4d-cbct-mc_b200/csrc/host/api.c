@@ -389,10 +389,12 @@ static int scan_report(scan_worker* w, int p, const uint64_t* image, double dt) 
   scan_shared* sh = w->sh;
   mcgpu_ctx* ctx = sh->ctx;
   const double t0 = now_s();
-  int rc = mcgpu_write_projection_ascii(ctx, p, image, dt);
+  int rc;
+  mcgpu_fail_into(w->err, sizeof w->err); /* the writers run on this worker's thread: their messages must not race on ctx->err */
+  rc = mcgpu_write_projection_ascii(ctx, p, image, dt);
   if (rc == MCGPU_OK && sh->write_raw) rc = mcgpu_write_projection_raw(ctx, p, image);
+  mcgpu_fail_into(NULL, 0);
   w->t_report += now_s() - t0;
-  if (rc != MCGPU_OK) snprintf(w->err, sizeof w->err, "%s", ctx->err);
   scan_publish(sh, p, rc == MCGPU_OK ? 1 : rc, dt);
   return rc;
 }

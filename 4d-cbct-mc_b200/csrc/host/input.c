@@ -9,13 +9,25 @@
 
 #include "mcgpu_host.h"
 
+/* Worker threads of a scan (api.c: scan_thread) report into their own buffer: the context's message buffer belongs to the
+ * caller's thread.  mcgpu_fail_into(buf) redirects the failures raised on THIS thread until it is reset with NULL. */
+static __thread char* tls_err_buf = NULL;
+static __thread size_t tls_err_len = 0;
+
+void mcgpu_fail_into(char* buf, size_t len) {
+  tls_err_buf = buf;
+  tls_err_len = buf ? len : 0;
+}
+
 int mcgpu_fail(mcgpu_ctx* ctx, int code, const char* fmt, ...) {
+  char* out = tls_err_buf ? tls_err_buf : ctx->err;
+  const size_t len = tls_err_buf ? tls_err_len : sizeof ctx->err;
   va_list ap;
   va_start(ap, fmt);
-  vsnprintf(ctx->err, sizeof ctx->err, fmt, ap);
+  vsnprintf(out, len, fmt, ap);
   va_end(ap);
   if (ctx->verbose) { /* the reference reports on stdout, where cbctmc greps for "error" (Q9) */
-    printf("\n\n   !!ERROR!! %s\n\n", ctx->err);
+    printf("\n\n   !!ERROR!! %s\n\n", out);
     fflush(stdout);
   }
   return code;

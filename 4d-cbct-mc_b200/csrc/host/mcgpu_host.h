@@ -168,6 +168,7 @@ void mcgpu_free_volume(mcgpu_volume* v);
 void mcgpu_free_tables(mcgpu_tables* t);
 void mcgpu_free_scene(mcgpu_scene* s);
 int mcgpu_fail(mcgpu_ctx* ctx, int code, const char* fmt, ...);
+void mcgpu_fail_into(char* buf, size_t len); /* failures raised on the calling thread go to buf instead of ctx->err (NULL: back to ctx->err) */
 void mcgpu_devices_ready(mcgpu_ctx* ctx); /* api.c: join the background device opens; call before touching ctx->dev / num_devices */
 /* grid of the projection(s) simulated last (or of the first one before any run): sticky hpt AND sticky history count */
 void mcgpu_current_grid(const mcgpu_ctx* ctx, int* hpt, int* blocks, unsigned long long* launched);

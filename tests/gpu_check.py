@@ -60,7 +60,10 @@ def compare_case(name, phantom, report, **cfg_kw):
     det_cm = (cfg.detector_size[0] / 10, cfg.detector_size[1] / 10)
     ok_all = True
     per_proj = []
-    for p in range(info.num_projections):
+    last_writer = {}
+    for p in range(info.num_projections):  # with specific angles later projections overwrite earlier files of the same name (Q7)
+        last_writer[Path(eng.projection_filename(p)).name] = p
+    for p in sorted(last_writer.values()):
         img = eng.run_projection(p)
         ms = eng.last_kernel_ms
         fname = Path(eng.projection_filename(p)).name
