@@ -62,7 +62,7 @@ extern "C" struct mcgpu_device* mcgpu_dev_open(int ordinal, char* err, size_t er
     const char* k = getenv("MCGPU_KERNEL");
     const char* t = getenv("MCGPU_W_THRESHOLD");
     d->kernel_generation = (k && atoi(k) == 1) ? 1 : (k && atoi(k) == 2) ? 2 : 3;
-    d->w_threshold = t ? atoi(t) : (d->kernel_generation == 3 ? 12 : 8);
+    d->w_threshold = t ? atoi(t) : (d->kernel_generation == 3 ? 16 : 8);  // r02e: 16 is 0.3-0.7 % ahead of 12 on every workload
     d->wf_rows = getenv("MCGPU_WF_ROWS") ? atoi(getenv("MCGPU_WF_ROWS")) : 0;
     if (d->wf_rows != 16 && d->wf_rows != 32) d->wf_rows = 0;
     d->wf_block = (getenv("MCGPU_WF_BLOCK") && atoi(getenv("MCGPU_WF_BLOCK")) == 1024) ? 1024 : 512;
