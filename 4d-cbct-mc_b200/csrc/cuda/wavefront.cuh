@@ -17,14 +17,14 @@
 // time and its stream is advanced strictly in order, so every float of every trajectory and hence
 // every integer tally is identical to generations 1 and 2 and to the reference (tested).
 //
-// Queues are rings of 16-bit ids in shared memory with two counters each: producers reserve `tail` with one
-// warp-aggregated atomicAdd per push and then write their entries (an entry is EMPTY until written); a popping
-// warp claims [head, head + n) with ONE atomicCAS on `head`, n <= tail - head, and reads its entries, waiting for
-// the few that are reserved but not written yet.  Two shared-memory atomics per batch exchange in total: the
-// exchange is a chain of dependent long-latency operations on the warp's critical path, and what it costs is that
-// latency (~600 issue slots per exchange beyond its ~230 instructions, measured through the tracking threshold:
-// DESIGN.md 10), not its instruction count.  No locks; all waits are bounded (a watchdog raises the launch's
-// error flag instead of hanging).
+// Queues are rings of 16-bit ids in shared memory: `tail` is reserved with one warp-aggregated atomicAdd per push,
+// entries are published individually (an entry is EMPTY until written), `avail` counts published entries and is
+// claimed with atomicCAS by the popping warp, `head` gives it its ring positions.  No locks; the only waits are on
+// an entry that is reserved but not yet written, and they are bounded (a watchdog raises the launch's error flag
+// instead of hanging).  A leaner protocol without `avail` (pop = one CAS on `head` against `tail`, two atomics per
+// exchange instead of four; git fa86281) was measured: +0.5 % on Catphan and thorax but -9 % on the air
+// scan, whose photons change queue twice per history -- popping warps then claim entries that are reserved but not
+// written yet and burn issue slots waiting for them (r02i, profiles/r02_experiments.txt).
 //
 // Code size is a first-class constraint here: with exact arithmetic the kernel was bound by instruction-
 // cache misses until its hot code fitted the SM's 32 KB instruction cache.  Hence ONE
@@ -48,8 +48,9 @@ enum WfQueue : int { Q_W = 0, Q_N = 1, Q_C = 2, Q_R = 3, Q_COUNT = 4 };
 enum WfField : int { F_X = 0, F_Y, F_Z, F_U, F_V, F_W, F_E, F_S1, F_S2, F_S0, F_HIST, F_META, F_MFPW };
 
 struct WfControl {
-  unsigned head[Q_COUNT];  // next ring position to pop (claimed by CAS)
-  unsigned tail[Q_COUNT];  // next ring position to push (reserved by atomicAdd); tail - head = entries waiting (written or about to be)
+  unsigned head[Q_COUNT];  // next ring position to pop
+  unsigned tail[Q_COUNT];  // next ring position to push (reserved by atomicAdd)
+  int avail[Q_COUNT];      // entries published and not yet claimed
   int live;          // contexts that still have work (not finished)
   int active_warps;  // warps that have not retired
   int phase;         // queue the CTA is draining (sticky scheduling)
@@ -118,6 +119,8 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
   if (threadIdx.x == 0) {
     for (int t = 0; t < Q_COUNT; t++) ctl->head[t] = 0u, ctl->tail[t] = 0u;
     ctl->tail[Q_N] = (unsigned)pool_size;
+    for (int t = 0; t < Q_COUNT; t++) ctl->avail[t] = 0;
+    ctl->avail[Q_N] = pool_size;
     ctl->live = pool_size;
     ctl->active_warps = (int)(blockDim.x >> 5);
     ctl->phase = Q_N;
@@ -128,8 +131,7 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
   const unsigned lt_mask = (1u << lane) - 1u;
   float* wbuf = sh_scratch + (threadIdx.x >> 5) * rows * stride;
   const long long n_streams = stream_end - stream_begin;
-  volatile unsigned* v_head = ctl->head;
-  volatile unsigned* v_tail = ctl->tail;
+  volatile int* v_avail = ctl->avail;
   volatile int* v_live = &ctl->live;
   volatile int* v_phase = &ctl->phase;
 
@@ -149,9 +151,7 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
     if (lane == 0) {
       int idle = 0;
       for (;;) {
-        // heads first, then tails: a tail read later can only be larger, so tail - head never overstates what the CAS below claims
-        const unsigned h0 = v_head[0], h1 = v_head[1], h2 = v_head[2], h3 = v_head[3];
-        const int a0 = (int)(v_tail[0] - h0), a1 = (int)(v_tail[1] - h1), a2 = (int)(v_tail[2] - h2), a3 = (int)(v_tail[3] - h3);
+        const int a0 = v_avail[0], a1 = v_avail[1], a2 = v_avail[2], a3 = v_avail[3];
         int best = -1, a = 0;
         {  // keep draining the queue the CTA is working on, then move to the fullest one: most warps of
            // the CTA run the same kind of code, which is what the SM's 32 KB instruction cache rewards
@@ -181,9 +181,9 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
           continue;
         }
         const int take = a < 32 ? a : 32;
-        const unsigned h = best == Q_W ? h0 : best == Q_N ? h1 : best == Q_C ? h2 : h3;
-        if (atomicCAS(&ctl->head[best], h, h + (unsigned)take) == h) {
-          q = best, n = take, pos = h;
+        if (atomicCAS(&ctl->avail[best], a, a - take) == a) {
+          q = best, n = take;
+          pos = atomicAdd(&ctl->head[best], (unsigned)take);
           break;
         }
       }
@@ -422,6 +422,9 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
         }
         *e = (unsigned short)pid;
       }
+      __threadfence_block();
+      __syncwarp();
+      if (nq >= 0 && (int)lane == leader) atomicAdd(&ctl->avail[nq], cnt);
     }
     {
       const unsigned m_f = __ballot_sync(MCGPU_FULL_MASK, act && state == ST_F);
