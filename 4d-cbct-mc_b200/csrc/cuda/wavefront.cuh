@@ -41,6 +41,9 @@ namespace MCGPU_NS {
 #define MCGPU_WF_FIELDS 13
 #define MCGPU_WF_STRIDE 13  // words per context in the pool: odd, so contexts spread over the shared-memory banks
 #define MCGPU_WF_MAX_POOL 2048
+#ifndef MCGPU_WF_CHAIN_MIN
+#define MCGPU_WF_CHAIN_MIN 24  // lanes of a batch that must want the same next kind of work for the warp to chain into it (33: never)
+#endif
 
 enum WfQueue : int { Q_W = 0, Q_N = 1, Q_C = 2, Q_R = 3, Q_COUNT = 4 };
 // F_MFPW: the Woodcock mean free path at the photon's energy (K:246-247), fetched when the photon enters the tracking state so
@@ -144,10 +147,24 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
 #else
 #define WF_STAT(x)
 #endif
+  // The batch a warp is working on lives in registers across iterations: after a source batch nearly every lane wants a tracking
+  // step, and after a tracking batch in an empty geometry (the air scan) every lane wants the tally -- the warp then CHAINS into that
+  // kind of work with the lanes it holds (the others are stored and pushed as usual) instead of pushing 32 ids and popping 32 others.
+  Photon p;
+  Ranecu rng;
+  int state = ST_F, slot = 0, scatter_state = 0, hist_left = 0, pid = 0;
+  float s0 = 0.f, mfpw = 0.f;
+  bool act = false, unsaved = false;  // unsaved: the lanes kept from the previous iteration hold fields their pool entries do not
+  int chain_q = -1;
   for (;;) {
-    // ------------------------------------------------------------------ acquire a batch: up to 32 ids of one queue
     int q = 0, n = 0;
+    if (chain_q >= 0) {
+      q = chain_q;
+      n = __popc(__ballot_sync(MCGPU_FULL_MASK, act));
+    } else {
+    // ------------------------------------------------------------------ acquire a batch: up to 32 ids of one queue
     unsigned pos = 0;
+    unsaved = false;
     if (lane == 0) {
       int idle = 0;
       for (;;) {
@@ -195,8 +212,8 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
     if (n <= 0) break;
     WF_STAT(st_pops[q]++; st_lanes[q] += n;)
 
-    bool act = (int)lane < n;
-    int pid = 0;
+    act = (int)lane < n;
+    pid = 0;
     if (act) {
       volatile unsigned short* e = rings + q * ring + ((pos + lane) & ring_mask);
       unsigned v;
@@ -216,10 +233,8 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
     __syncwarp();
     __threadfence_block();
 
-    Photon p;
-    Ranecu rng;
-    int state = ST_F, slot = 0, scatter_state = 0, hist_left = 0;
-    float s0 = 0.f, mfpw = 0.f;
+    state = ST_F, slot = 0, scatter_state = 0, hist_left = 0;
+    s0 = 0.f, mfpw = 0.f;
     p.x = p.y = p.z = p.u = p.v = p.w = p.E = 0.f;
     rng.s1 = rng.s2 = 1;
     if (act) {  // one load / store site for every kind of batch keeps the code small (the kernel is instruction-cache bound)
@@ -231,6 +246,7 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
       hist_left = PI(F_HIST);
       mfpw = PF(F_MFPW);
     }
+    }  // acquired or chained
 
     if (q == Q_W) {
       // ---------------------------------------------------------------- W: delta-tracking steps (K:249-279)
@@ -390,20 +406,34 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
       }
     }
 
-    // ------------------------------------------------------------------ store what every kind changes, hand the ids on
-    if (act) {
+    // ------------------------------------------------------------------ chain, or store what every kind changes and hand the ids on
+    int nq = !act || state == ST_F ? -1 : state == ST_W ? Q_W : (state == ST_C || state == ST_CT) ? Q_C : state == ST_R ? Q_R : Q_N;
+    chain_q = -1;
+    if (q == Q_N || q == Q_W) {  // source -> tracking, tracking -> tally: keep going with the lanes that want it when they are >= 3/4 of a warp
+      const int want = q == Q_N ? Q_W : Q_N;
+      if (__popc(__ballot_sync(MCGPU_FULL_MASK, nq == want)) >= MCGPU_WF_CHAIN_MIN) chain_q = want;
+    }
+    const bool keep = chain_q >= 0 && nq == chain_q;
+    {
+      const unsigned m_f = __ballot_sync(MCGPU_FULL_MASK, act && state == ST_F);
+      if (m_f && lane == 0) atomicSub(&ctl->live, __popc(m_f));
+    }
+    if (act && !keep) {
       PF(F_X) = p.x, PF(F_Y) = p.y, PF(F_Z) = p.z;
       PI(F_S1) = rng.s1, PI(F_S2) = rng.s2;
       PI(F_META) = wf_pack_meta(state, scatter_state, slot);
-      if (q != Q_W) {  // a tracking batch moves the photon and draws random numbers; direction, energy, S0 and the history count stay
+      if (q != Q_W || unsaved) {  // a tracking batch moves the photon and draws random numbers; direction, energy, S0 and the history count stay
         PF(F_U) = p.u, PF(F_V) = p.v, PF(F_W) = p.w, PF(F_E) = p.E;
         PF(F_S0) = s0;
         PI(F_HIST) = hist_left;
         PF(F_MFPW) = mfpw;
       }
     }
+    if (keep) nq = -1;  // not pushed
+    act = keep;
+    if (chain_q >= 0) unsaved = true;
+    if (__all_sync(MCGPU_FULL_MASK, nq < 0)) continue;  // nothing to hand on
     __threadfence_block();
-    const int nq = !act || state == ST_F ? -1 : state == ST_W ? Q_W : (state == ST_C || state == ST_CT) ? Q_C : state == ST_R ? Q_R : Q_N;
     {  // lanes bound for the same queue find each other with one match: one reservation per queue, no loop over queues
       const unsigned peers = __match_any_sync(MCGPU_FULL_MASK, nq);
       const int leader = __ffs(peers) - 1, cnt = __popc(peers);
@@ -425,10 +455,6 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
       __threadfence_block();
       __syncwarp();
       if (nq >= 0 && (int)lane == leader) atomicAdd(&ctl->avail[nq], cnt);
-    }
-    {
-      const unsigned m_f = __ballot_sync(MCGPU_FULL_MASK, act && state == ST_F);
-      if (m_f && lane == 0) atomicSub(&ctl->live, __popc(m_f));
     }
   }
 #ifdef MCGPU_WF_STATS
