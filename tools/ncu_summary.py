@@ -18,6 +18,9 @@ WANT = [
     "l1tex__t_set_accesses_pipe_lsu_mem_global_op_red.sum", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_xu.sum", "sm__inst_executed_pipe_fp64.sum", "sm__inst_executed_pipe_lsu.sum", "sm__inst_executed_pipe_alu.sum",
     "sm__inst_executed_pipe_fma.sum", "sm__inst_executed_pipe_fmaheavy.sum",
+    # collected with --metrics next to --set full (tools/gpu_r02_l.sh): L2 sectors, atomics, instruction caches
+    "lts__t_sectors.sum", "lts__t_sectors_op_read.sum", "lts__t_sectors_op_atom.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__t_set_accesses_pipe_lsu_mem_global_op_atom.sum", "sm__icc_request_hit_rate.pct", "gcc__cache_requests_type_instruction.sum.pct_of_peak_sustained_elapsed",
 ]
 STALLS = "smsp__average_warps_issue_stalled_{}_per_issue_active.ratio"
 REASONS = ["long_scoreboard", "short_scoreboard", "wait", "math_pipe_throttle", "branch_resolving", "no_instruction", "not_selected", "selected", "dispatch_stall",
