@@ -9,7 +9,7 @@
 // = one RANECU stream and the photon it is tracking, 12 words at an odd stride of 13) and four queues of context ids, one
 // per kind of work:
 //   Q_W  delta-tracking steps                       Q_N  tally / next stream / next history (source)
-//   Q_C  Compton (S0 for fresh events + one tau trial)   Q_R  Rayleigh
+//   Q_C  Compton (S0 for fresh events + one tau trial)   Q_R  Rayleigh      Q_I  next RANECU stream
 // A warp repeatedly pops up to 32 ids from ONE queue, loads those contexts into registers, runs
 // that kind of work for all lanes (the same code as generation 2's phases), stores the contexts and
 // pushes every id to the queue of its new state.  Because a queue collects the photons of 512
@@ -45,7 +45,10 @@ namespace MCGPU_NS {
 #define MCGPU_WF_CHAIN_MIN 24  // lanes of a batch that must want the same next kind of work for the warp to chain into it (33: never)
 #endif
 
-enum WfQueue : int { Q_W = 0, Q_N = 1, Q_C = 2, Q_R = 3, Q_COUNT = 4 };
+// Q_I: contexts whose RANECU stream is used up (or not assigned yet).  Re-initialising a generator costs ~700 instructions; done
+// inside a tally/source batch it ran for the one or two lanes that needed it while the rest of the warp waited (2.6 % of Catphan's
+// instructions at 1.2 lanes, r02l); collected in their own queue, 32 generators are re-initialised together.
+enum WfQueue : int { Q_W = 0, Q_N = 1, Q_C = 2, Q_R = 3, Q_I = 4, Q_COUNT = 5 };
 // F_MFPW: the Woodcock mean free path at the photon's energy (K:246-247), fetched when the photon enters the tracking state so
 // that a tracking batch starts without a dependent L2 access
 enum WfField : int { F_X = 0, F_Y, F_Z, F_U, F_V, F_W, F_E, F_S1, F_S2, F_S0, F_HIST, F_META, F_MFPW };
@@ -109,11 +112,11 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
   for (int i = threadIdx.x; i < sc.num_slots * MCGPU_MAX_SHELLS; i += blockDim.x) sh_shells[i] = sc.cmp_shells[i];
   if (BITS == 4 || BITS == 8)
     for (int i = threadIdx.x; i < sc.palette_size; i += blockDim.x) sh_palette[i] = sc.palette[i];
-  // every context starts in Q_N asking for a stream
+  // every context starts in Q_I asking for a stream
   for (int i = threadIdx.x; i < Q_COUNT * ring; i += blockDim.x) rings[i] = MCGPU_WF_EMPTY;
   __syncthreads();
   for (int i = threadIdx.x; i < pool_size; i += blockDim.x) {
-    rings[Q_N * ring + i] = (unsigned short)i;
+    rings[Q_I * ring + i] = (unsigned short)i;
     for (int k = 0; k < MCGPU_WF_STRIDE; k++) pool_i[i * MCGPU_WF_STRIDE + k] = 0;
     pool_i[i * MCGPU_WF_STRIDE + F_META] = wf_pack_meta(ST_I, 0, 0);
     pool_i[i * MCGPU_WF_STRIDE + F_S1] = 1;
@@ -121,12 +124,12 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
   }
   if (threadIdx.x == 0) {
     for (int t = 0; t < Q_COUNT; t++) ctl->head[t] = 0u, ctl->tail[t] = 0u;
-    ctl->tail[Q_N] = (unsigned)pool_size;
+    ctl->tail[Q_I] = (unsigned)pool_size;
     for (int t = 0; t < Q_COUNT; t++) ctl->avail[t] = 0;
-    ctl->avail[Q_N] = pool_size;
+    ctl->avail[Q_I] = pool_size;
     ctl->live = pool_size;
     ctl->active_warps = (int)(blockDim.x >> 5);
-    ctl->phase = Q_N;
+    ctl->phase = Q_I;
   }
   __syncthreads();
 
@@ -142,7 +145,7 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
 #define PI(f) pool_i[pid * MCGPU_WF_STRIDE + (f)]
 
 #ifdef MCGPU_WF_STATS  // diagnostics build (make ... XFLAGS=-DMCGPU_WF_STATS): batch sizes per queue, tracking steps, idle polls
-  unsigned long long st_pops[Q_COUNT] = {0, 0, 0, 0}, st_lanes[Q_COUNT] = {0, 0, 0, 0}, st_wsteps = 0, st_wlanes = 0, st_idle = 0;
+  unsigned long long st_pops[Q_COUNT] = {0, 0, 0, 0, 0}, st_lanes[Q_COUNT] = {0, 0, 0, 0, 0}, st_wsteps = 0, st_wlanes = 0, st_idle = 0;
 #define WF_STAT(x) x
 #else
 #define WF_STAT(x)
@@ -168,18 +171,20 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
     if (lane == 0) {
       int idle = 0;
       for (;;) {
-        const int a0 = v_avail[0], a1 = v_avail[1], a2 = v_avail[2], a3 = v_avail[3];
+        const int a0 = v_avail[0], a1 = v_avail[1], a2 = v_avail[2], a3 = v_avail[3], a4 = v_avail[4];
         int best = -1, a = 0;
         {  // keep draining the queue the CTA is working on, then move to the fullest one: most warps of
            // the CTA run the same kind of code, which is what the SM's 32 KB instruction cache rewards
           const int ph = *v_phase;
-          const int ap = ph == Q_W ? a0 : ph == Q_N ? a1 : ph == Q_C ? a2 : a3;
-          if (ap >= 32) best = ph, a = ap;
+          const int ap = ph == Q_W ? a0 : ph == Q_N ? a1 : ph == Q_C ? a2 : ph == Q_R ? a3 : a4;
+          if (a4 >= 32) best = Q_I, a = a4;  // a full batch of used-up streams: those contexts do nothing until they are served
+          else if (ap >= 32) best = ph, a = ap;
           else {
             if (a0 > a) best = Q_W, a = a0;
             if (a1 > a) best = Q_N, a = a1;
             if (a2 > a) best = Q_C, a = a2;
             if (a3 > a) best = Q_R, a = a3;
+            if (a4 > a) best = Q_I, a = a4;
             if (best >= 0 && best != ph) *v_phase = best;
           }
         }
@@ -205,9 +210,9 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
         }
       }
     }
-    {  // one broadcast: queue (2 bits), count (6 bits), ring position (the rings have at most 2048 entries)
-      const unsigned packed = __shfl_sync(MCGPU_FULL_MASK, (unsigned)q | ((unsigned)n << 2) | ((pos & (unsigned)ring_mask) << 8), 0);
-      q = (int)(packed & 3u), n = (int)((packed >> 2) & 63u), pos = packed >> 8;
+    {  // one broadcast: queue (3 bits), count (6 bits), ring position (the rings have at most 2048 entries)
+      const unsigned packed = __shfl_sync(MCGPU_FULL_MASK, (unsigned)q | ((unsigned)n << 3) | ((pos & (unsigned)ring_mask) << 9), 0);
+      q = (int)(packed & 7u), n = (int)((packed >> 3) & 63u), pos = packed >> 9;
     }
     if (n <= 0) break;
     WF_STAT(st_pops[q]++; st_lanes[q] += n;)
@@ -304,26 +309,7 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
           tally_photon<ROT>(sc, vw, p, scatter_state);
           state = ST_N;
         }
-        {  // next stream of the launch (K:198)
-          const bool want = (state == ST_N && hist_left == 0) || state == ST_I;
-          const unsigned m_i = __ballot_sync(MCGPU_FULL_MASK, want);
-          if (m_i) {
-            unsigned long long base = 0;
-            const int leader = __ffs(m_i) - 1;
-            if ((int)lane == leader) base = atomicAdd(stream_counter, (unsigned long long)__popc(m_i));
-            base = __shfl_sync(MCGPU_FULL_MASK, base, leader);
-            if (want) {
-              const long long s = (long long)base + __popc(m_i & lt_mask);
-              if (s < n_streams) {
-                ranecu_init(rng, stream_begin + s, seed_input, g1, g2);
-                hist_left = histories_per_thread;
-                state = ST_N;
-              } else {
-                state = ST_F;
-              }
-            }
-          }
-        }
+        if (state == ST_N && hist_left == 0) state = ST_I;  // the stream is used up: the next one is assigned in a Q_I batch
         if (state == ST_N) {  // K:210-234
           hist_left--;
           const bool enters = emit_photon<ROT>(sc, vw, st, rng, p);
@@ -335,6 +321,23 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
           }
         }
         if (__popc(__ballot_sync(MCGPU_FULL_MASK, state == ST_T)) < thr) break;
+      }
+    } else if (q == Q_I) {
+      // ---------------------------------------------------------------- I: next stream of the launch (K:198), RANECU jump-ahead (K:841-894)
+      const unsigned m_i = __ballot_sync(MCGPU_FULL_MASK, act);
+      unsigned long long base = 0;
+      const int leader = __ffs(m_i) - 1;
+      if ((int)lane == leader) base = atomicAdd(stream_counter, (unsigned long long)__popc(m_i));
+      base = __shfl_sync(MCGPU_FULL_MASK, base, leader);
+      if (act) {
+        const long long s = (long long)base + __popc(m_i & lt_mask);
+        if (s < n_streams) {
+          ranecu_init(rng, stream_begin + s, seed_input, g1, g2);
+          hist_left = histories_per_thread;
+          state = ST_N;
+        } else {
+          state = ST_F;
+        }
       }
     } else {
       // ---------------------------------------------------------------- C / CT / R: one scattering step
@@ -407,9 +410,9 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
     }
 
     // ------------------------------------------------------------------ chain, or store what every kind changes and hand the ids on
-    int nq = !act || state == ST_F ? -1 : state == ST_W ? Q_W : (state == ST_C || state == ST_CT) ? Q_C : state == ST_R ? Q_R : Q_N;
+    int nq = !act || state == ST_F ? -1 : state == ST_W ? Q_W : (state == ST_C || state == ST_CT) ? Q_C : state == ST_R ? Q_R : state == ST_I ? Q_I : Q_N;
     chain_q = -1;
-    if (q == Q_N || q == Q_W) {  // source -> tracking, tracking -> tally: keep going with the lanes that want it when they are >= 3/4 of a warp
+    if (q == Q_N || q == Q_W || q == Q_I) {  // new stream -> source -> tracking, tracking -> tally: keep going with the lanes that want it when they are >= 3/4 of a warp
       const int want = q == Q_N ? Q_W : Q_N;
       if (__popc(__ballot_sync(MCGPU_FULL_MASK, nq == want)) >= MCGPU_WF_CHAIN_MIN) chain_q = want;
     }
@@ -460,7 +463,7 @@ __global__ void __launch_bounds__(MCGPU_WF_MAX_BLOCK, 1)
 #ifdef MCGPU_WF_STATS
   if (lane == 0) {
     unsigned long long* g = stream_counter + 2;
-    for (int t = 0; t < Q_COUNT; t++) atomicAdd(g + t, st_pops[t]), atomicAdd(g + 4 + t, st_lanes[t]);
+    for (int t = 0; t < 4; t++) atomicAdd(g + t, st_pops[t]), atomicAdd(g + 4 + t, st_lanes[t]);
     atomicAdd(g + 8, st_wsteps), atomicAdd(g + 9, st_wlanes), atomicAdd(g + 10, st_idle);
   }
 #endif
