@@ -8,7 +8,7 @@
 // How: a CTA of 16 warps owns a POOL of photon contexts in shared memory (2 per thread; a context
 // = one RANECU stream and the photon it is tracking, 12 words at an odd stride of 13) and four queues of context ids, one
 // per kind of work:
-//   Q_W  delta-tracking steps                       Q_N  tally / next stream / next history (source)
+//   Q_W  delta-tracking steps                       Q_N  tally / next history (source)
 //   Q_C  Compton (S0 for fresh events + one tau trial)   Q_R  Rayleigh      Q_I  next RANECU stream
 // A warp repeatedly pops up to 32 ids from ONE queue, loads those contexts into registers, runs
 // that kind of work for all lanes (the same code as generation 2's phases), stores the contexts and
