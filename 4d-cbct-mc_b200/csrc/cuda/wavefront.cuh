@@ -6,7 +6,7 @@
 // kernel is issue-bound, so idle lanes are the loss that is left.
 //
 // How: a CTA of 16 warps owns a POOL of photon contexts in shared memory (2 per thread; a context
-// = one RANECU stream and the photon it is tracking, 12 words at an odd stride of 13) and four queues of context ids, one
+// = one RANECU stream and the photon it is tracking, 13 words) and five queues of context ids, one
 // per kind of work:
 //   Q_W  delta-tracking steps                       Q_N  tally / next history (source)
 //   Q_C  Compton (S0 for fresh events + one tau trial)   Q_R  Rayleigh      Q_I  next RANECU stream
