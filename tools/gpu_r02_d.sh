@@ -1,6 +1,7 @@
 #!/bin/bash
 # Round-2 GPU session D (one B200): wavefront diagnostics (batch sizes per queue), experiment builds, statistical protocol,
 # final ncu captures of the shipped kernel, gpu_check.
+# (needs the diagnostics and experiment libraries of that session: `make stats`; lib_x1 = make BUILD=build_x1 LIBDIR=4d-cbct-mc_b200/lib_x1 XFLAGS=-DMCGPU_EXP_UNROLL2 lib, a switch since removed)
 set -u
 O=gpurun_out/r02d
 mkdir -p $O

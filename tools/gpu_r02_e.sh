@@ -1,5 +1,6 @@
 #!/bin/bash
 # Round-2 GPU session E (one B200): parity + speed after the queue protocol change (two atomics per exchange, Woodcock MFP in the context).
+# (needs `make stats` for the wf_stats step)
 set -u
 O=gpurun_out/r02e
 mkdir -p $O

@@ -1,5 +1,6 @@
 #!/bin/bash
 # quick A/B (one B200): MFP record prefetched at batch start (product) vs fetched on demand (lib_x2)
+# (lib_x2 was the shipped source with -DMCGPU_NO_REC_PREFETCH while the prefetch was in the source; both the prefetch and the switch have been removed, see wavefront.cuh)
 set -u
 O=gpurun_out/r02f
 mkdir -p $O

@@ -1,6 +1,7 @@
 #!/bin/bash
 # one B200: queue-protocol A/B (product: head CAS + tail add | x3: published counter, 4 atomics | x4: product + sleep in the entry wait),
 # the bench's clock sampler fix, ncu of the line-pair workload
+# (lib_x3 / lib_x4 were built from git fa86281..1c0ec66 with -DMCGPU_WF_PUBLISHED / -DMCGPU_WF_SPIN_SLEEP=40; the shipped source is the x3 protocol)
 set -u
 O=gpurun_out/r02i
 mkdir -p $O

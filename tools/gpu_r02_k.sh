@@ -1,5 +1,6 @@
 #!/bin/bash
 # one B200: phase chaining (source -> tracking, tracking -> tally without a queue exchange) -- parity, then A/B against the same kernel without it (lib_x5)
+# (lib_x5 = make BUILD=build_x5 LIBDIR=4d-cbct-mc_b200/lib_x5 XFLAGS=-DMCGPU_WF_CHAIN_MIN=33 lib: the shipped kernel with phase chaining switched off)
 set -u
 O=gpurun_out/r02k
 mkdir -p $O
