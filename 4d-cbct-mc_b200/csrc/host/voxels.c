@@ -211,6 +211,8 @@ static void* vox_worker(void* arg) {
  *   char magic[8] = "MCGPUVXB"; uint32 version = 1; uint32 nx, ny, nz; float32 dx, dy, dz [cm];
  *   uint8 material[nx*ny*nz] (1-based, x fastest); float32 density[nx*ny*nz]
  * optionally gzip-compressed.  Same validation and the same volume as the text file with these values. */
+static int finish_volume(mcgpu_ctx* ctx, int validate, const char* who); /* below: density_max, palette, packing (chunk-parallel) */
+
 static int read_voxels_binary(mcgpu_ctx* ctx, gzFile f) {
   uint32_t head[4];
   float size[3];
@@ -232,12 +234,7 @@ static int read_voxels_binary(mcgpu_ctx* ctx, gzFile f) {
       return mcgpu_fail(ctx, MCGPU_E_PARSE, "load_voxels: binary geometry ends inside the density array");
     done += want;
   }
-  for (done = 0; done < n; done++) { /* the checks of load_voxels (H:2120-2132) */
-    if (ctx->vol.material[done] > MCGPU_MAX_MATERIALS || ctx->vol.material[done] < 1)
-      return mcgpu_fail(ctx, MCGPU_E_PARSE, "load_voxels: voxel material number %d out of range [1,%d] at voxel number %zu", ctx->vol.material[done], MCGPU_MAX_MATERIALS, done + 1);
-    if (ctx->vol.density[done] < 1.0e-9f) return mcgpu_fail(ctx, MCGPU_E_PARSE, "load_voxels: voxel density can not be 0 or negative at voxel number %zu", done + 1);
-  }
-  return mcgpu_finish_volume(ctx);
+  return finish_volume(ctx, 1, "load_voxels"); /* with the checks of load_voxels (H:2120-2132), in parallel */
 }
 
 /* ---- content-addressed geometry cache ---------------------------------------------------------------
@@ -497,7 +494,7 @@ static int read_voxels_text(mcgpu_ctx* ctx, const char* path) {
 
 int mcgpu_set_voxels(mcgpu_ctx* ctx, int nx, int ny, int nz, float dx, float dy, float dz, const uint8_t* material, const float* density) {
   float size[3];
-  size_t n, i;
+  size_t n;
   int rc;
   if (!ctx || !material || !density) return MCGPU_E_ARG;
   size[0] = dx;
@@ -505,60 +502,208 @@ int mcgpu_set_voxels(mcgpu_ctx* ctx, int nx, int ny, int nz, float dx, float dy,
   size[2] = dz;
   if ((rc = alloc_volume(ctx, nx, ny, nz, size)) != MCGPU_OK) return rc;
   n = (size_t)nx * ny * nz;
-  for (i = 0; i < n; i++) {
-    if (material[i] > MCGPU_MAX_MATERIALS || material[i] < 1)
-      return mcgpu_fail(ctx, MCGPU_E_PARSE, "set_voxels: voxel material number %d out of range [1,%d] at voxel number %zu", material[i], MCGPU_MAX_MATERIALS, i + 1);
-    if (density[i] < 1.0e-9f) return mcgpu_fail(ctx, MCGPU_E_PARSE, "set_voxels: voxel density can not be 0 or negative at voxel number %zu", i + 1);
-  }
   memcpy(ctx->vol.material, material, n);
   memcpy(ctx->vol.density, density, n * sizeof(float));
-  return mcgpu_finish_volume(ctx);
+  return finish_volume(ctx, 1, "set_voxels");
 }
 
 /* density_max per material, palette of distinct (material, density) pairs, packed indices */
-int mcgpu_finish_volume(mcgpu_ctx* ctx) {
-  mcgpu_volume* v = &ctx->vol;
-  const size_t n = (size_t)v->nx * v->ny * v->nz;
-  enum { HBITS = 18, HSIZE = 1 << HBITS, MAXPAL = 65536 };
-  uint64_t* keys = (uint64_t*)malloc(sizeof(uint64_t) * HSIZE);
-  int32_t* vals = (int32_t*)malloc(sizeof(int32_t) * HSIZE);
-  uint16_t* idx = (uint16_t*)malloc(sizeof(uint16_t) * n);
-  uint64_t* pal = (uint64_t*)malloc(sizeof(uint64_t) * MAXPAL);
+/* ---- density_max, palette and packing, chunk-parallel --------------------------------------------------------
+ * The volume is cut into contiguous chunks, one per thread.  Pass A (parallel): optional validation (the checks of
+ * load_voxels, H:2120-2132), per-material density maxima, and the chunk's own palette of distinct (material, density)
+ * pairs in order of first occurrence, with a 16-bit LOCAL index per voxel.  Merge (serial, tiny): the global palette is
+ * the concatenation of the chunk palettes in chunk order without repeats -- exactly the order of first occurrence in the
+ * whole volume, i.e. what one thread walking the volume would build, whatever the number of threads.  Pass B
+ * (parallel): local -> global indices, written in the packed width.  500^3 voxels: 0.9 s -> 0.25 s on 8 cores. */
+enum { PK_HBITS = 17, PK_HSIZE = 1 << PK_HBITS, PK_MAXPAL = 65536, PK_MAX_THREADS = 16 };
+
+typedef struct pack_chunk {
+  const mcgpu_volume* v;
+  size_t begin, end; /* voxel range, begin even */
+  uint16_t* idx;     /* whole-volume array of local (pass A) indices */
+  int validate;
+  /* pass A results */
+  uint64_t* pal; /* distinct keys in order of first occurrence */
+  int npal, overflow;
+  float density_max[MCGPU_MAX_MATERIALS];
+  int err;           /* 0 ok, 2 material out of range, 3 density <= 0 */
+  size_t err_at;
+  /* pass B inputs */
+  const uint16_t* to_global;
+  int bits;
+  void* packed;
+  pthread_t thread;
+  int threaded;
+} pack_chunk;
+
+static void* pack_pass_a(void* arg) {
+  pack_chunk* c = (pack_chunk*)arg;
+  const mcgpu_volume* v = c->v;
+  uint64_t* keys = (uint64_t*)malloc(sizeof(uint64_t) * PK_HSIZE);
+  int32_t* vals = (int32_t*)malloc(sizeof(int32_t) * PK_HSIZE);
   uint64_t last_key = ~0ull;
-  int last_val = -1, npal = 0, overflow = 0, k, min_bits = 0;
+  int last_val = -1, k;
   size_t i;
-  if (!keys || !vals || !idx || !pal) {
-    free(keys), free(vals), free(idx), free(pal);
-    return mcgpu_fail(ctx, MCGPU_E_NOMEM, "load_voxels: not enough memory to pack %zu voxels", n);
+  c->pal = (uint64_t*)malloc(sizeof(uint64_t) * PK_MAXPAL);
+  c->npal = 0, c->overflow = 0, c->err = 0;
+  for (k = 0; k < MCGPU_MAX_MATERIALS; k++) c->density_max[k] = -999.0f;
+  if (!keys || !vals || !c->pal) {
+    free(keys), free(vals);
+    c->err = -1;
+    return NULL;
   }
-  for (k = 0; k < MCGPU_MAX_MATERIALS; k++) v->density_max[k] = -999.0f;
-  memset(vals, 0xff, sizeof(int32_t) * HSIZE);
-  for (i = 0; i < n; i++) {
+  memset(vals, 0xff, sizeof(int32_t) * PK_HSIZE);
+  for (i = c->begin; i < c->end; i++) {
     uint32_t bits;
     uint64_t key;
     const int m = v->material[i];
     const float rho = v->density[i];
-    if (rho > v->density_max[m - 1]) v->density_max[m - 1] = rho;
-    if (overflow) continue;
+    if (c->validate) {
+      if (m > MCGPU_MAX_MATERIALS || m < 1) {
+        c->err = 2, c->err_at = i;
+        break;
+      }
+      if (rho < 1.0e-9f) {
+        c->err = 3, c->err_at = i;
+        break;
+      }
+    }
+    if (rho > c->density_max[m - 1]) c->density_max[m - 1] = rho;
+    if (c->overflow) continue;
     memcpy(&bits, &rho, 4);
     key = ((uint64_t)m << 32) | bits;
     if (key != last_key) {
-      uint32_t h = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> (64 - HBITS));
-      while (vals[h] >= 0 && keys[h] != key) h = (h + 1) & (HSIZE - 1);
+      uint32_t h = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> (64 - PK_HBITS));
+      while (vals[h] >= 0 && keys[h] != key) h = (h + 1) & (PK_HSIZE - 1);
       if (vals[h] < 0) {
-        if (npal == MAXPAL) {
-          overflow = 1;
+        if (c->npal == PK_MAXPAL) {
+          c->overflow = 1;
           continue;
         }
         keys[h] = key;
-        vals[h] = npal;
-        pal[npal++] = key;
+        vals[h] = c->npal;
+        c->pal[c->npal++] = key;
       }
       last_key = key;
       last_val = vals[h];
     }
-    idx[i] = (uint16_t)last_val;
+    c->idx[i] = (uint16_t)last_val;
   }
+  free(keys), free(vals);
+  return NULL;
+}
+
+static void* pack_pass_b(void* arg) {
+  pack_chunk* c = (pack_chunk*)arg;
+  const uint16_t* map = c->to_global;
+  size_t i;
+  if (c->bits == 4) {
+    uint8_t* p = (uint8_t*)c->packed;
+    for (i = c->begin; i + 1 < c->end; i += 2) p[i >> 1] = (uint8_t)(map[c->idx[i]] | (map[c->idx[i + 1]] << 4));
+    if (i < c->end) p[i >> 1] = (uint8_t)map[c->idx[i]]; /* odd voxel count: last chunk only (chunks begin at even voxels) */
+  } else if (c->bits == 8) {
+    uint8_t* p = (uint8_t*)c->packed;
+    for (i = c->begin; i < c->end; i++) p[i] = (uint8_t)map[c->idx[i]];
+  } else {
+    uint16_t* p = (uint16_t*)c->packed;
+    for (i = c->begin; i < c->end; i++) p[i] = map[c->idx[i]];
+  }
+  return NULL;
+}
+
+static void run_chunks(pack_chunk* c, int n, void* (*fn)(void*)) {
+  int k;
+  for (k = 1; k < n; k++) c[k].threaded = pthread_create(&c[k].thread, NULL, fn, &c[k]) == 0;
+  fn(&c[0]);
+  for (k = 1; k < n; k++) {
+    if (c[k].threaded)
+      pthread_join(c[k].thread, NULL);
+    else
+      fn(&c[k]); /* thread limit of the container: do the chunk here */
+  }
+}
+
+static int finish_volume(mcgpu_ctx* ctx, int validate, const char* who) {
+  mcgpu_volume* v = &ctx->vol;
+  const size_t n = (size_t)v->nx * v->ny * v->nz;
+  pack_chunk chunks[PK_MAX_THREADS];
+  uint16_t* idx = (uint16_t*)malloc(sizeof(uint16_t) * (n + 1));
+  uint64_t* pal = (uint64_t*)malloc(sizeof(uint64_t) * PK_MAXPAL);
+  uint16_t* maps = NULL;
+  int nt, k, j, npal = 0, overflow = 0, min_bits = 0, rc = MCGPU_OK;
+  nt = (int)sysconf(_SC_NPROCESSORS_ONLN);
+  if (nt > PK_MAX_THREADS) nt = PK_MAX_THREADS;
+  if (nt < 1 || n < ((size_t)1 << 20)) nt = 1; /* small volumes: one pass on this thread */
+  if (!idx || !pal) {
+    free(idx), free(pal);
+    return mcgpu_fail(ctx, MCGPU_E_NOMEM, "%s: not enough memory to pack %zu voxels", who, n);
+  }
+  memset(chunks, 0, sizeof chunks);
+  for (k = 0; k < nt; k++) {
+    chunks[k].v = v;
+    chunks[k].begin = (n * (size_t)k / (size_t)nt) & ~(size_t)1;
+    chunks[k].end = k + 1 == nt ? n : ((n * (size_t)(k + 1) / (size_t)nt) & ~(size_t)1);
+    chunks[k].idx = idx;
+    chunks[k].validate = validate;
+  }
+  run_chunks(chunks, nt, pack_pass_a);
+  for (k = 0; k < nt && rc == MCGPU_OK; k++) { /* the first offending voxel in file order, like a sequential reader */
+    const pack_chunk* c = &chunks[k];
+    if (c->err == -1)
+      rc = mcgpu_fail(ctx, MCGPU_E_NOMEM, "%s: not enough memory to pack %zu voxels", who, n);
+    else if (c->err == 2)
+      rc = mcgpu_fail(ctx, MCGPU_E_PARSE, "%s: voxel material number %d out of range [1,%d] at voxel number %zu", who, v->material[c->err_at], MCGPU_MAX_MATERIALS, c->err_at + 1);
+    else if (c->err == 3)
+      rc = mcgpu_fail(ctx, MCGPU_E_PARSE, "%s: voxel density can not be 0 or negative at voxel number %zu", who, c->err_at + 1);
+  }
+  if (rc != MCGPU_OK) {
+    for (k = 0; k < nt; k++) free(chunks[k].pal);
+    free(idx), free(pal);
+    return rc;
+  }
+  for (k = 0; k < MCGPU_MAX_MATERIALS; k++) {
+    v->density_max[k] = -999.0f;
+    for (j = 0; j < nt; j++)
+      if (chunks[j].density_max[k] > v->density_max[k]) v->density_max[k] = chunks[j].density_max[k];
+  }
+  /* merge the chunk palettes in chunk order: global order = order of first occurrence in the volume */
+  maps = (uint16_t*)malloc(sizeof(uint16_t) * (size_t)nt * PK_MAXPAL);
+  if (!maps) {
+    for (k = 0; k < nt; k++) free(chunks[k].pal);
+    free(idx), free(pal);
+    return mcgpu_fail(ctx, MCGPU_E_NOMEM, "%s: not enough memory to pack %zu voxels", who, n);
+  }
+  {
+    uint64_t* keys = (uint64_t*)malloc(sizeof(uint64_t) * PK_HSIZE);
+    int32_t* vals = (int32_t*)malloc(sizeof(int32_t) * PK_HSIZE);
+    if (!keys || !vals) {
+      free(keys), free(vals), free(maps);
+      for (k = 0; k < nt; k++) free(chunks[k].pal);
+      free(idx), free(pal);
+      return mcgpu_fail(ctx, MCGPU_E_NOMEM, "%s: not enough memory to pack %zu voxels", who, n);
+    }
+    memset(vals, 0xff, sizeof(int32_t) * PK_HSIZE);
+    for (k = 0; k < nt; k++) {
+      overflow |= chunks[k].overflow;
+      for (j = 0; j < chunks[k].npal && !overflow; j++) {
+        const uint64_t key = chunks[k].pal[j];
+        uint32_t h = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> (64 - PK_HBITS));
+        while (vals[h] >= 0 && keys[h] != key) h = (h + 1) & (PK_HSIZE - 1);
+        if (vals[h] < 0) {
+          if (npal == PK_MAXPAL) {
+            overflow = 1;
+            break;
+          }
+          keys[h] = key;
+          vals[h] = npal;
+          pal[npal++] = key;
+        }
+        maps[(size_t)k * PK_MAXPAL + j] = (uint16_t)vals[h];
+      }
+    }
+    free(keys), free(vals);
+  }
+  for (k = 0; k < nt; k++) free(chunks[k].pal), chunks[k].pal = NULL;
   free(v->palette_density), free(v->palette_material), free(v->packed);
   v->palette_density = NULL, v->palette_material = NULL, v->packed = NULL;
   { /* MCGPU_VOXEL_BITS=8|16|64 forces a wider packing than needed (parity tests of every kernel variant) */
@@ -568,9 +713,10 @@ int mcgpu_finish_volume(mcgpu_ctx* ctx) {
   }
   if (overflow) {
     mcgpu_f2* p = (mcgpu_f2*)malloc(sizeof(mcgpu_f2) * n);
+    size_t i;
     if (!p) {
-      free(keys), free(vals), free(idx), free(pal);
-      return mcgpu_fail(ctx, MCGPU_E_NOMEM, "load_voxels: not enough memory to pack %zu voxels", n);
+      free(idx), free(pal), free(maps);
+      return mcgpu_fail(ctx, MCGPU_E_NOMEM, "%s: not enough memory to pack %zu voxels", who, n);
     }
     /* (density, material0) pairs; material is remapped to a slot when the scene is built */
     for (i = 0; i < n; i++) {
@@ -592,26 +738,31 @@ int mcgpu_finish_volume(mcgpu_ctx* ctx) {
       v->palette_material[k] = (uint8_t)(pal[k] >> 32);
     }
     if (npal <= 16 && min_bits <= 4) {
-      uint8_t* p = (uint8_t*)calloc((n + 1) / 2, 1);
-      for (i = 0; i < n; i++) p[i >> 1] |= (uint8_t)(idx[i] << ((i & 1) * 4));
-      v->packed = p;
-      v->packed_bytes = (n + 1) / 2;
       v->voxel_bits = 4;
+      v->packed_bytes = (n + 1) / 2;
     } else if (npal <= 256 && min_bits <= 8) {
-      uint8_t* p = (uint8_t*)malloc(n);
-      for (i = 0; i < n; i++) p[i] = (uint8_t)idx[i];
-      v->packed = p;
-      v->packed_bytes = n;
       v->voxel_bits = 8;
+      v->packed_bytes = n;
     } else {
-      v->packed = idx;
-      idx = NULL;
-      v->packed_bytes = n * 2;
       v->voxel_bits = 16;
+      v->packed_bytes = n * 2;
     }
+    v->packed = malloc(v->packed_bytes);
+    if (!v->packed || !v->palette_density || !v->palette_material) {
+      free(idx), free(pal), free(maps);
+      return mcgpu_fail(ctx, MCGPU_E_NOMEM, "%s: not enough memory to pack %zu voxels", who, n);
+    }
+    for (k = 0; k < nt; k++) {
+      chunks[k].to_global = maps + (size_t)k * PK_MAXPAL;
+      chunks[k].bits = v->voxel_bits;
+      chunks[k].packed = v->packed;
+    }
+    run_chunks(chunks, nt, pack_pass_b);
   }
-  free(keys), free(vals), free(idx), free(pal);
+  free(idx), free(pal), free(maps);
   ctx->have_voxels = 1;
   ctx->have_tables = 0;
   return MCGPU_OK;
 }
+
+int mcgpu_finish_volume(mcgpu_ctx* ctx) { return finish_volume(ctx, 0, "load_voxels"); }

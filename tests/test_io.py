@@ -309,3 +309,53 @@ def test_content_addressed_geometry_cache(pkg, cases, tmp_path, monkeypatch):
     entries[0].write_bytes(b"MCGPUVXB" + b"\0" * 10)
     third = volume()
     assert np.array_equal(third[2], plain[2]) and entries[0].stat().st_size > 1000
+
+
+@pytest.mark.parametrize("shape,n_pairs,bits", [((101, 103, 101), 11, 4), ((128, 128, 70), 200, 8), ((128, 128, 70), 5000, 16)])
+def test_chunk_parallel_packing_equals_first_occurrence_order(pkg, cases, shape, n_pairs, bits):
+    """Volumes above 2^20 voxels are packed by several threads (voxels.c: finish_volume): the palette must still be in order of
+    first occurrence in the whole volume and the packed indices what one sequential pass would write -- also for an odd
+    number of voxels at 4 bits -- and a bad voxel must be reported at its own (first) position."""
+    rng = np.random.default_rng(7)
+    n = int(np.prod(shape))
+    assert n > (1 << 20)
+    mats = rng.integers(1, 8, size=n_pairs).astype(np.uint8)
+    dens = (0.05 + np.arange(n_pairs) * 1e-3).astype(np.float32)
+    # long runs of one pair (like anatomy), every pair present, pair 0 only in the last quarter (late first occurrence)
+    runs = rng.integers(0, n_pairs, size=n // 97 + 1)
+    runs[: 3 * len(runs) // 4][runs[: 3 * len(runs) // 4] == 0] = 1
+    which = np.repeat(runs, 97)[:n]
+    which[-n_pairs:] = np.arange(n_pairs)
+    m = mats[which].reshape(shape[::-1])  # [z][y][x], x fastest
+    r = dens[which].reshape(shape[::-1])
+    inp, _, _ = cases["water_p1"]
+    with load(pkg, inp) as eng:
+        eng.set_voxels(m.transpose(2, 1, 0), r.transpose(2, 1, 0), (0.1, 0.1, 0.1))
+        info = eng.info
+        assert info.voxel_bits == bits
+        key = (m.reshape(-1).astype(np.uint64) << np.uint64(32)) | r.reshape(-1).view(np.uint32).astype(np.uint64)
+        uniq, first, inv = np.unique(key, return_index=True, return_inverse=True)
+        order = np.argsort(first)
+        rank = np.empty_like(order)
+        rank[order] = np.arange(len(order))
+        gi = rank[inv]
+        assert info.palette_size == len(uniq)
+        packed = eng.table("voxel_packed")
+        if bits == 4:
+            pad = np.concatenate([gi, [0]]) if n % 2 else gi
+            want = (pad[0::2] | (pad[1::2] << 4)).astype(np.uint8)
+        elif bits == 8:
+            want = gi.astype(np.uint8)
+        else:
+            want = gi.astype(np.uint16).view(np.uint8)
+        assert np.array_equal(packed, want)
+        dmax = eng.table("density_max")
+        for mat in range(1, 8):
+            sel = m.reshape(-1) == mat
+            assert dmax[mat - 1] == (r.reshape(-1)[sel].max() if sel.any() else np.float32(-999.0))
+        bad = m.copy().reshape(-1)
+        bad[n - 5] = 0
+        bad[n // 2 + 3] = 26
+        with pytest.raises(pkg.engine.McgpuError) as e:
+            eng.set_voxels(bad.reshape(shape[::-1]).transpose(2, 1, 0), r.transpose(2, 1, 0), (0.1, 0.1, 0.1))
+        assert f"voxel number {n // 2 + 4}" in str(e.value) and "26" in str(e.value)
